@@ -1,0 +1,174 @@
+"""Pin the oracle against the UNMODIFIED reference and write tests/golden/*.npz.
+
+TEST INFRASTRUCTURE ONLY.  Runs only in the build container (needs /root/reference); the
+fixtures it writes are committed so the GPU box never needs the reference.
+
+    python -m oracle.make_golden            # check + (re)write fixtures
+
+What is pinned (reference file -> oracle function -> fixture):
+  gmm_waymo/src/gmm_impl.py::train_gmm (diag, spherical)  -> flat_gmm.py_train_gmm     -> flat_py_*.npz
+  gmm_waymo/src/gmm_impl.py::predict                      -> flat_gmm.py_predict       -> (same)
+  hgmm/hgmm_cupy_cpu_working.py::buildGMMTree             -> hgmm_tree.build_gmm_tree  -> tree_build_*.npz
+  hgmm/hgmm_cupy_cpu_working.py::gmmTreeRegESTep, GMMTree.maximization_step/.registration
+                                                          -> registration.*            -> tree_reg_*.npz
+  gmmreg_gpu/cost_functions.py::RigidCostFunction         -> l2reg.rigid_cost          -> l2_cost.npz
+Also converts data/bun000.ply, data/bun045.ply vertices to float32 .npy (inputs of configs 1,2,4).
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+sys.path.insert(0, ROOT)
+np.infty = np.inf      # removed in NumPy 2; used at gmm_waymo/src/gmm_impl.py:120
+
+from oracle import flat_gmm, hgmm_tree, registration as oreg  # noqa: E402
+from oracle.plyio import read_ply_vertices                    # noqa: E402
+
+
+def load_ref_flat():
+    sys.path.insert(0, os.path.join(REF, "src/python/gmm_waymo/src"))
+    import gmm_impl
+    return gmm_impl
+
+
+def load_ref_hgmm_cpu():
+    """exec lines 1-431 of hgmm_cupy_cpu_working.py (everything above the script-level driver)."""
+    path = os.path.join(REF, "src/python/hgmm/hgmm_cupy_cpu_working.py")
+    src = "\n".join(open(path).read().split("\n")[:431])
+    ns = {"__name__": "ref_hgmm_cpu"}
+    exec(compile(src, path, "exec"), ns)
+    return ns
+
+
+def quiet(fn, *a, **k):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        return fn(*a, **k)
+
+
+def check(name, got, want, tol):
+    e = flat_gmm.rel_fro(got, want)
+    status = "ok " if e <= tol else "FAIL"
+    print("  [%s] %-34s rel_fro = %.3e (tol %.0e)" % (status, name, e, tol))
+    if e > tol:
+        raise SystemExit("oracle disagrees with the reference: " + name)
+    return e
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    bun0 = read_ply_vertices(os.path.join(REF, "data/bun000.ply"))
+    bun45 = read_ply_vertices(os.path.join(REF, "data/bun045.ply"))
+    assert bun0.shape == (40256, 3) and bun45.shape == (40097, 3)
+    np.save(os.path.join(GOLD, "bun000_xyz.npy"), bun0)
+    np.save(os.path.join(GOLD, "bun045_xyz.npy"), bun45)
+
+    # ---------------- flat, python variant (config 1) ----------------
+    ref = load_ref_flat()
+    print("flat / gmm_waymo train_gmm")
+    for cov_type in ("diag", "spherical"):
+        for (tag, X, J, seed) in (("sub4k_J8", bun0[::10], 8, 0), ("bun000_J8", bun0, 8, 0), ("sub4k_J32", bun0[::10], 32, 3)):
+            rng = np.random.default_rng(seed)
+            means0 = X[rng.choice(X.shape[0], J, replace=False)].astype(np.float32)
+            covs0 = (0.1 * np.ones((J, 3) if cov_type == "diag" else (J,))).astype(np.float32)
+            w0 = (np.ones(J) / J).astype(np.float32)
+            # the reference run in its own float32 (what users see) and in float64 (the pin: the same
+            # code is dtype-generic, and its float32 self differs from its float64 self by up to ~1e-3)
+            r32 = quiet(ref.train_gmm, X.astype(np.float32), 10, 0.0, means0, covs0, w0, cov_type)
+            r_inv, r_mu, r_w, r_cov, r_ll = quiet(ref.train_gmm, X.astype(np.float64), 10, 0.0, means0.astype(np.float64),
+                                                  covs0.astype(np.float64), w0.astype(np.float64), cov_type)
+            o_inv, o_mu, o_w, o_cov, o_ll = flat_gmm.py_train_gmm(X, 10, 0.0, means0, covs0, w0, cov_type)
+            check("%s %s means" % (cov_type, tag), o_mu, r_mu, 1e-10)
+            check("%s %s covs" % (cov_type, tag), o_cov, r_cov, 1e-10)
+            check("%s %s weights" % (cov_type, tag), o_w, r_w, 1e-10)
+            # the reference rounds log(2 pi) to float32 even in float64 runs (gmm_impl.py:64,78): ~3e-8 on the log-lik only
+            check("%s %s loglik" % (cov_type, tag), o_ll, np.array(r_ll, dtype=np.float64), 1e-7)
+            print("       reference float32 vs its float64 self: means %.1e covs %.1e weights %.1e" % (
+                flat_gmm.rel_fro(r32[1], r_mu), flat_gmm.rel_fro(r32[3], r_cov), flat_gmm.rel_fro(r32[2], r_w)))
+            r_lab = ref.predict(X.astype(np.float64), r_inv, r_mu, r_w, cov_type)
+            o_lab = flat_gmm.py_predict(X.astype(np.float64), o_inv, o_mu, o_w, cov_type)
+            agree = float((r_lab == o_lab).mean())
+            print("       predict agreement %.5f" % agree)
+            assert agree == 1.0
+            np.savez_compressed(os.path.join(GOLD, "flat_py_%s_%s.npz" % (cov_type, tag)),
+                                stride=np.int64(10 if tag.startswith("sub4k") else 1), J=np.int64(J),
+                                means0=means0, covs0=covs0, weights0=w0,
+                                ref_means=r_mu, ref_covs=r_cov, ref_weights=r_w, ref_inv_cov=r_inv,
+                                ref_ll=np.array(r_ll, dtype=np.float64), ref32_means=r32[1], ref32_covs=r32[3], ref32_weights=r32[2],
+                                oracle_means=o_mu, oracle_covs=o_cov, oracle_weights=o_w,
+                                oracle_inv_cov=o_inv, oracle_ll=np.array(o_ll), ref_labels=r_lab.astype(np.int32))
+
+    # ---------------- tree build (CPU file) ----------------
+    print("tree / hgmm_cupy_cpu_working buildGMMTree")
+    ns = load_ref_hgmm_cpu()
+    for (tag, X, L, ls) in (("bun1500_L2", bun0[::26][:1500].astype(np.float64), 2, 80.0),
+                           ("bun600_L2", bun0[::67][:600].astype(np.float64), 2, 20.0)):
+        nt = hgmm_tree.n_total(L)
+        nodes = quiet(ns["buildGMMTree"], X, L, ls, 1.0e-4)
+        r_pi = np.array([float(np.ravel(n.mixingCoeff)[0]) for n in nodes])
+        r_mu = np.array([np.ravel(n.mean) for n in nodes], dtype=np.float64)
+        r_cov = np.array([np.asarray(n.covar, dtype=np.float64).reshape(3, 3) for n in nodes])
+        idx = hgmm_tree.reference_init_indices(L, flavor="cpu")
+        init_means = X[idx]
+        o_pi, o_mu, o_cov, o_cur, o_iters, o_trace = hgmm_tree.build_gmm_tree(
+            X, L, ls, 1.0e-4, init_means, sig2=0.00034, ll_mode="level", return_trace=True)
+        print("       oracle iterations per level:", o_iters)
+        check("%s pi" % tag, o_pi, r_pi, 1e-6)
+        check("%s mu" % tag, o_mu, r_mu, 1e-6)
+        check("%s cov" % tag, o_cov, r_cov, 1e-6)
+        np.savez_compressed(os.path.join(GOLD, "tree_build_%s.npz" % tag), points=X, L=np.int64(L), ls=np.float64(ls),
+                            ld=np.float64(1e-4), sig2=np.float64(0.00034), init_means=init_means,
+                            ref_pi=r_pi, ref_mu=r_mu, ref_cov=r_cov, oracle_iters=np.array(o_iters),
+                            oracle_current=o_cur)
+
+        # ---------------- registration on the same tree ----------------
+        if tag == "bun1500_L2":
+            th = np.deg2rad(8.0)
+            Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+            T = (X @ Rz.T + np.array([0.004, -0.003, 0.002]))[::2]
+            gt = ns["GMMTree"](None, tree_level=L, lambda_c=0.01)
+            gt._source = X
+            gt._nodes = nodes
+            est = quiet(gt.expectation_step, T)
+            rm0 = np.array([float(m.zero) for m in est.moments])
+            rm1 = np.array([np.ravel(m.one) for m in est.moments], dtype=np.float64)
+            om0, om1, om2 = oreg.reg_e_step(T, r_pi, r_mu, r_cov, L, 0.01)
+            check("reg E-step M0", om0, rm0, 1e-9)
+            check("reg E-step M1", om1, rm1, 1e-9)
+            res = quiet(gt.maximization_step, est, gt._tf_result)
+            oR, ot, oq, ox = oreg.reg_m_step_lstsq(om0, om1, r_pi, r_mu, r_cov, np.identity(3), np.zeros(3))
+            check("reg M-step rot", oR, res.transformation.rot, 1e-9)
+            check("reg M-step t", ot, res.transformation.t, 1e-9)
+            check("reg M-step q", oq, res.q, 1e-9)
+            H, g, c = oreg.reg_normal_equations(om0, om1, r_mu, r_cov)
+            xn = np.linalg.solve(H, g)
+            check("normal-eq twist == lstsq twist", xn, ox, 1e-7)
+            check("normal-eq residual == lstsq q", [c - g @ xn], oq, 1e-6)
+            gt2 = ns["GMMTree"](None, tree_level=L, lambda_c=0.01)
+            gt2._source = X
+            gt2._nodes = nodes
+            full = quiet(gt2.registration, T, 20, 1.0e-4)
+            fR, ft, fq, fit = oreg.registration(T, r_pi, r_mu, r_cov, L, 0.01, 20, 1.0e-4)
+            check("registration rot", fR, full.transformation.rot, 1e-8)
+            check("registration t", ft, full.transformation.t, 1e-8)
+            print("       registration iterations (oracle) %d, recovered angle %.3f deg" %
+                  (fit, np.rad2deg(np.arccos((np.trace(fR) - 1) / 2))))
+            np.savez_compressed(os.path.join(GOLD, "tree_reg_bun1500_L2.npz"), target=T, L=np.int64(L), lambda_c=np.float64(0.01),
+                                pi=r_pi, mu=r_mu, cov=r_cov, ref_M0=rm0, ref_M1=rm1,
+                                ref_step_rot=res.transformation.rot, ref_step_t=res.transformation.t,
+                                ref_step_q=np.ravel(res.q), ref_rot=full.transformation.rot, ref_t=full.transformation.t,
+                                ref_q=np.ravel(full.q), oracle_iters=np.int64(fit), true_rot=Rz)
+    print("golden fixtures written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
