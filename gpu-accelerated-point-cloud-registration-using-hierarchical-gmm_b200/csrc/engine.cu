@@ -1,0 +1,791 @@
+// engine.cu -- host side of libhgmm: context, buffers, EM / registration drivers, NCCL, C ABI.
+//
+// Host drivers replaced (paths relative to the reference checkout):
+//   GMM::solve                          src/c++/gmm_fit/gmm_kernels.cu:371-504
+//   train_gmm                           src/python/gmm_waymo/src/gmm_impl.py:118-145
+//   buildGMMTree                        src/python/hgmm/hgmm_gpu.py:466-548
+//   GMMTree.registration                src/python/hgmm/hgmm_gpu.py:754-768
+// The reference syncs the device 3x and copies weights back every EM iteration and mallocs inside
+// the loop (gmm_kernels.cu:304-350,455-481); here everything is enqueued on one stream, the
+// stopping rules run on the device, and the host only polls a 2-int control word.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace hgmm;
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen (no link-time dependency; single-GPU use never touches it)
+// ------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+struct ncclUniqueId128 { char internal[128]; };
+typedef int (*fn_ncclGetUniqueId)(ncclUniqueId128*);
+typedef int (*fn_ncclCommInitRank)(ncclComm_t*, int, ncclUniqueId128, int);
+typedef int (*fn_ncclCommDestroy)(ncclComm_t);
+typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef const char* (*fn_ncclGetErrorString)(int);
+struct NcclApi {
+    void* lib = nullptr;
+    fn_ncclGetUniqueId GetUniqueId = nullptr;
+    fn_ncclCommInitRank CommInitRank = nullptr;
+    fn_ncclCommDestroy CommDestroy = nullptr;
+    fn_ncclAllReduce AllReduce = nullptr;
+    fn_ncclGetErrorString GetErrorString = nullptr;
+    std::string err;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+bool nccl_load() {
+    if (g_nccl.AllReduce) return true;
+    const char* env = getenv("HGMM_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        if (!nm) continue;
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) {
+        g_nccl.err = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?");
+        return false;
+    }
+    g_nccl.GetUniqueId = (fn_ncclGetUniqueId)dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (fn_ncclCommInitRank)dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (fn_ncclCommDestroy)dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (fn_ncclAllReduce)dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.GetErrorString = (fn_ncclGetErrorString)dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+        g_nccl.err = "libnccl is missing a required symbol";
+        g_nccl.AllReduce = nullptr;
+        return false;
+    }
+    return true;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+}  // namespace
+
+struct hgmm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    std::string err;
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms[3] = {0, 0, 0};
+
+    // points (this rank's shard), SoA
+    int n = 0;
+    int64_t n_total = 0;
+    DevBuf bx, by, bz, stage;
+
+    // shared small state
+    DevBuf acc;          // doubles: [kAccHdr + count*kMom]
+    DevBuf ctrl;         // 8 ints
+    DevBuf qstate;       // 4 doubles
+    DevBuf hist;         // doubles (ll / q history)
+    int* h_ctrl = nullptr;      // pinned, 8 ints
+    double* h_dbl = nullptr;    // pinned, 64 doubles
+
+    // flat model
+    FlatModel fm{};
+    bool have_flat = false;
+    DevBuf f_means, f_covs, f_weights, f_invcov, f_packed, labels;
+
+    // tree model + work
+    TreeModel tm{};
+    bool have_tree = false;
+    DevBuf t_pi, t_mu, t_cov, t_cplx, t_packed, t_init;
+    DevBuf wx[2], wy[2], wz[2], wperm[2], wpnode[2], wslot[2], wcpar[2], wcstart[2], wclen[2];
+    DevBuf p_group, p_tilecnt, p_tileoff, p_segbase, p_seg0, p_seg1, p_chunkcnt, p_chunkoff, nchunks, current;
+
+    // registration
+    int nt_pts = 0;
+    DevBuf tx, ty, tz, racc, Rt;
+    bool have_target = false;
+    bool have_racc = false;
+
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            char b__[512];                                                                        \
+            snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            ctx->err = b__;                                                                       \
+            return HGMM_ERR_CUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+#define FAIL(code, msg)      \
+    do {                     \
+        ctx->err = (msg);    \
+        return (code);       \
+    } while (0)
+
+static int allreduce(hgmm_ctx* ctx, double* buf, size_t count) {
+    if (!ctx->comm || ctx->nranks <= 1) return HGMM_OK;
+    int r = g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+    if (r != 0) {
+        ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        return HGMM_ERR_NCCL;
+    }
+    return HGMM_OK;
+}
+
+static int64_t level_base_h(int l) {
+    int64_t p = 1;
+    for (int i = 0; i < l; ++i) p *= 8;
+    return 8 * (p - 1) / 7;
+}
+static int64_t level_count_h(int l) {
+    int64_t p = 8;
+    for (int i = 0; i < l; ++i) p *= 8;
+    return p;
+}
+
+extern "C" {
+
+const char* hgmm_version(void) { return "hgmm-b200 0.1 (sm_100a)"; }
+
+int64_t hgmm_tree_total_nodes(int32_t max_level) { return max_level < 0 ? 0 : level_base_h(max_level); }
+
+int hgmm_create(hgmm_ctx** out, int device, void* stream) {
+    if (!out) return HGMM_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return HGMM_ERR_CUDA;   // no silent CPU fallback
+    if (device < 0 || device >= count) return HGMM_ERR_INVALID;
+    hgmm_ctx* ctx = new hgmm_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return HGMM_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return HGMM_ERR_CUDA; }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HGMM_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    if (cudaMallocHost((void**)&ctx->h_ctrl, 8 * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_dbl, 64 * sizeof(double)) != cudaSuccess || ctx->ctrl.ensure(8 * sizeof(int)) != cudaSuccess ||
+        ctx->qstate.ensure(4 * sizeof(double)) != cudaSuccess || ctx->nchunks.ensure(sizeof(int)) != cudaSuccess ||
+        ctx->Rt.ensure(12 * sizeof(double)) != cudaSuccess) {
+        hgmm_destroy(ctx);
+        return HGMM_ERR_CUDA;
+    }
+    *out = ctx;
+    return HGMM_OK;
+}
+
+int hgmm_destroy(hgmm_ctx* ctx) {
+    if (!ctx) return HGMM_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    DevBuf* all[] = {&ctx->bx, &ctx->by, &ctx->bz, &ctx->stage, &ctx->acc, &ctx->ctrl, &ctx->qstate, &ctx->hist, &ctx->f_means,
+                     &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
+                     &ctx->t_cplx, &ctx->t_packed, &ctx->t_init, &ctx->p_group, &ctx->p_tilecnt, &ctx->p_tileoff, &ctx->p_segbase,
+                     &ctx->p_seg0, &ctx->p_seg1, &ctx->p_chunkcnt, &ctx->p_chunkoff, &ctx->nchunks, &ctx->current, &ctx->tx, &ctx->ty,
+                     &ctx->tz, &ctx->racc, &ctx->Rt};
+    for (DevBuf* b : all) b->release();
+    for (int i = 0; i < 2; ++i) {
+        DevBuf* w[] = {&ctx->wx[i], &ctx->wy[i], &ctx->wz[i], &ctx->wperm[i], &ctx->wpnode[i], &ctx->wslot[i], &ctx->wcpar[i],
+                       &ctx->wcstart[i], &ctx->wclen[i]};
+        for (DevBuf* b : w) b->release();
+    }
+    if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
+    if (ctx->h_dbl) cudaFreeHost(ctx->h_dbl);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return HGMM_OK;
+}
+
+const char* hgmm_last_error(const hgmm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t hgmm_launch_count(const hgmm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t hgmm_total_points(const hgmm_ctx* ctx) { return ctx ? ctx->n_total : 0; }
+
+// host/device AoS cloud -> device SoA
+static int upload_cloud(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind, DevBuf& X, DevBuf& Y, DevBuf& Z,
+                        const double* Rt_dev) {
+    if (n < 0 || n > 2000000000LL) FAIL(HGMM_ERR_INVALID, "point count out of range");
+    if (n > 0 && !xyz) FAIL(HGMM_ERR_INVALID, "null point pointer");
+    CK(cudaSetDevice(ctx->device));
+    const size_t fb = (size_t)(n > 0 ? n : 1) * sizeof(float);
+    CK(X.ensure(fb));
+    CK(Y.ensure(fb));
+    CK(Z.ensure(fb));
+    if (n == 0) return HGMM_OK;
+    const float* src = xyz;
+    if (mem_kind == HGMM_MEM_HOST) {
+        CK(ctx->stage.ensure(3 * fb));
+        CK(cudaMemcpyAsync(ctx->stage.p, xyz, 3 * fb, cudaMemcpyHostToDevice, ctx->stream));
+        src = ctx->stage.as<float>();
+    } else if (mem_kind != HGMM_MEM_DEVICE) {
+        FAIL(HGMM_ERR_INVALID, "mem_kind must be HGMM_MEM_HOST or HGMM_MEM_DEVICE");
+    }
+    if (Rt_dev) launch_aos_to_soa_transform(src, n, Rt_dev, X.as<float>(), Y.as<float>(), Z.as<float>(), ctx->stream);
+    else launch_aos_to_soa(src, n, X.as<float>(), Y.as<float>(), Z.as<float>(), ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return HGMM_OK;
+}
+
+int hgmm_set_points(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    int r = upload_cloud(ctx, xyz, n, mem_kind, ctx->bx, ctx->by, ctx->bz, nullptr);
+    if (r != HGMM_OK) return r;
+    ctx->n = (int)n;
+    ctx->n_total = n;
+    if (ctx->comm && ctx->nranks > 1) {
+        // total point count over ranks (the tree's pi = M0 / N_total, hgmm_gpu.py:257)
+        double* d = ctx->qstate.as<double>();
+        ctx->h_dbl[0] = (double)n;
+        CK(cudaMemcpyAsync(d, ctx->h_dbl, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        r = allreduce(ctx, d, 1);
+        if (r != HGMM_OK) return r;
+        CK(cudaMemcpyAsync(ctx->h_dbl, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->n_total = (int64_t)(ctx->h_dbl[0] + 0.5);
+    }
+    return HGMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// flat fit
+// ------------------------------------------------------------------------------------------
+static size_t cov_elems(int cov_type) { return cov_type == HGMM_COV_FULL ? 9 : (cov_type == HGMM_COV_DIAG ? 3 : 1); }
+
+int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_means, const float* init_covs,
+                  const float* init_weights, float* out_means, float* out_covs, float* out_weights, float* out_inv_cov,
+                  double* out_ll, int32_t* out_iters) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!cfg || !init_means || !init_covs || !init_weights) FAIL(HGMM_ERR_INVALID, "null config / init pointer");
+    if (ctx->n <= 0) FAIL(HGMM_ERR_STATE, "hgmm_set_points has not been called");
+    const int J = cfg->n_components;
+    if (J < 1 || J > kMaxFlatJ) FAIL(HGMM_ERR_INVALID, "n_components must be in [1, 1024] (use the tree for more)");
+    if (cfg->max_iter < 0 || cfg->max_iter > 1000000) FAIL(HGMM_ERR_INVALID, "bad max_iter");
+    if (cfg->flavor == HGMM_FLAVOR_CPP && cfg->cov_type != HGMM_COV_FULL) FAIL(HGMM_ERR_INVALID, "CPP flavour is full-covariance");
+    if (cfg->flavor == HGMM_FLAVOR_PY && cfg->cov_type == HGMM_COV_FULL) FAIL(HGMM_ERR_INVALID, "PY flavour is diag/spherical");
+    if (cfg->flavor != HGMM_FLAVOR_CPP && cfg->flavor != HGMM_FLAVOR_PY) FAIL(HGMM_ERR_INVALID, "unknown flavor");
+    CK(cudaSetDevice(ctx->device));
+    const int Jp = (J + 31) / 32 * 32;
+    const size_t ce = cov_elems(cfg->cov_type);
+    CK(ctx->f_means.ensure((size_t)Jp * 3 * sizeof(float)));
+    CK(ctx->f_covs.ensure((size_t)Jp * 9 * sizeof(float)));
+    CK(ctx->f_weights.ensure((size_t)Jp * sizeof(float)));
+    CK(ctx->f_invcov.ensure((size_t)Jp * 3 * sizeof(float)));
+    CK(ctx->f_packed.ensure((size_t)Jp * sizeof(PackedComp)));
+    const size_t acc_n = kAccHdr + (size_t)Jp * kMom;
+    CK(ctx->acc.ensure(acc_n * sizeof(double)));
+    CK(ctx->hist.ensure((size_t)(cfg->max_iter + 1) * sizeof(double)));
+    FlatModel& m = ctx->fm;
+    m.J = J; m.Jp = Jp; m.cov_type = cfg->cov_type; m.flavor = cfg->flavor; m.sigma_bug = cfg->sigma_bug; m.tol = cfg->tol;
+    m.means = ctx->f_means.as<float>(); m.covs = ctx->f_covs.as<float>(); m.weights = ctx->f_weights.as<float>();
+    m.inv_cov = ctx->f_invcov.as<float>(); m.packed = ctx->f_packed.as<PackedComp>();
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(m.means, init_means, (size_t)J * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m.covs, init_covs, (size_t)J * ce * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m.weights, init_weights, (size_t)J * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->acc.p, 0, acc_n * sizeof(double), s));
+    CK(cudaMemsetAsync(ctx->ctrl.p, 0, 8 * sizeof(int), s));
+    launch_flat_pack(m, 1, s);
+    ctx->launches += 1;
+    const int tile = flat_pick_tile(ctx->n, ctx->num_sms, cfg->tile_points);
+    CK(cudaEventRecord(ctx->ev0, s));
+    for (int it = 0; it < cfg->max_iter; ++it) {
+        CK(launch_em_flat(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, ctx->acc.as<double>(),
+                          ctx->ctrl.as<int>(), ctx->num_sms, tile, s));
+        int r = allreduce(ctx, ctx->acc.as<double>(), kAccHdr + (size_t)J * kMom);
+        if (r != HGMM_OK) return r;
+        launch_flat_finalize(m, ctx->acc.as<double>(), ctx->ctrl.as<int>(), ctx->hist.as<double>(), (double)ctx->n_total, s);
+        ctx->launches += 2;
+    }
+    CK(cudaEventRecord(ctx->ev1, s));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out_means) CK(cudaMemcpyAsync(out_means, m.means, (size_t)J * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (out_covs) CK(cudaMemcpyAsync(out_covs, m.covs, (size_t)J * ce * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (out_weights) CK(cudaMemcpyAsync(out_weights, m.weights, (size_t)J * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (out_inv_cov && cfg->flavor == HGMM_FLAVOR_PY)
+        CK(cudaMemcpyAsync(out_inv_cov, m.inv_cov, (size_t)J * (ce == 1 ? 1 : 3) * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (out_ll && cfg->max_iter > 0)
+        CK(cudaMemcpyAsync(out_ll, ctx->hist.p, (size_t)cfg->max_iter * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (out_iters) *out_iters = ctx->h_ctrl[1];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms[0] = ms; ctx->last_ms[1] = ms; ctx->last_ms[2] = 0;
+    ctx->have_flat = true;
+    return HGMM_OK;
+}
+
+int hgmm_predict_flat(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind, int32_t* labels) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!ctx->have_flat) FAIL(HGMM_ERR_STATE, "no flat model: call hgmm_fit_flat first");
+    if (!labels) FAIL(HGMM_ERR_INVALID, "null labels");
+    CK(cudaSetDevice(ctx->device));
+    const float *x, *y, *z;
+    int np;
+    if (xyz) {
+        int r = upload_cloud(ctx, xyz, n, mem_kind, ctx->tx, ctx->ty, ctx->tz, nullptr);
+        if (r != HGMM_OK) return r;
+        ctx->have_target = false;
+        x = ctx->tx.as<float>(); y = ctx->ty.as<float>(); z = ctx->tz.as<float>();
+        np = (int)n;
+    } else {
+        x = ctx->bx.as<float>(); y = ctx->by.as<float>(); z = ctx->bz.as<float>();
+        np = ctx->n;
+    }
+    if (np <= 0) return HGMM_OK;
+    CK(ctx->labels.ensure((size_t)np * sizeof(int32_t)));
+    CK(launch_predict(x, y, z, np, ctx->fm.packed, ctx->fm.Jp, ctx->labels.as<int32_t>(), ctx->num_sms, ctx->stream));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(labels, ctx->labels.p, (size_t)np * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HGMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// tree
+// ------------------------------------------------------------------------------------------
+static int ensure_tree_model(hgmm_ctx* ctx, int L) {
+    if (L < 1 || L > 6) FAIL(HGMM_ERR_INVALID, "max_level must be in [1, 6]");
+    const int64_t nt = level_base_h(L);
+    CK(ctx->t_pi.ensure((size_t)nt * sizeof(float)));
+    CK(ctx->t_mu.ensure((size_t)nt * 3 * sizeof(float)));
+    CK(ctx->t_cov.ensure((size_t)nt * 9 * sizeof(float)));
+    CK(ctx->t_cplx.ensure((size_t)nt * sizeof(float)));
+    CK(ctx->t_packed.ensure((size_t)nt * sizeof(PackedComp)));
+    TreeModel& t = ctx->tm;
+    t.L = L; t.nt = (int)nt;
+    t.pi = ctx->t_pi.as<float>(); t.mu = ctx->t_mu.as<float>(); t.cov = ctx->t_cov.as<float>();
+    t.cplx = ctx->t_cplx.as<float>(); t.packed = ctx->t_packed.as<PackedComp>();
+    return HGMM_OK;
+}
+
+int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_means, float* out_pi, float* out_mu,
+                  float* out_cov, int64_t* out_current, int32_t* out_iters, double* out_q) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!cfg || !init_means) FAIL(HGMM_ERR_INVALID, "null config / init_means");
+    if (ctx->n <= 0) FAIL(HGMM_ERR_STATE, "hgmm_set_points has not been called");
+    CK(cudaSetDevice(ctx->device));
+    const int L = cfg->max_level;
+    int r = ensure_tree_model(ctx, L);
+    if (r != HGMM_OK) return r;
+    TreeModel& t = ctx->tm;
+    const int n = ctx->n;
+    cudaStream_t s = ctx->stream;
+    int chunk = cfg->chunk_points;
+    if (chunk <= 0) {
+        chunk = (int)(((int64_t)n / ((int64_t)ctx->num_sms * 16) + 31) / 32 * 32);
+        if (chunk < 128) chunk = 128;
+        if (chunk > 1024) chunk = 1024;
+    }
+    if (chunk % 32 != 0 || chunk > 65536) FAIL(HGMM_ERR_INVALID, "chunk_points must be a multiple of 32");
+    const int max_iters = cfg->max_iters_per_level > 0 ? cfg->max_iters_per_level : 10000;
+
+    // buffers
+    const int64_t leaf_parents = L >= 2 ? level_count_h(L - 2) : 1;       // parents of the deepest partition's output
+    const int64_t max_parents = L >= 2 ? level_count_h(L - 2) : 1;        // segments entering the last partition
+    const int64_t max_newseg = 8 * max_parents;
+    const int64_t max_chunks = (n + chunk - 1) / chunk + max_newseg + 8;
+    (void)leaf_parents;
+    for (int i = 0; i < 2; ++i) {
+        CK(ctx->wx[i].ensure((size_t)n * 4)); CK(ctx->wy[i].ensure((size_t)n * 4)); CK(ctx->wz[i].ensure((size_t)n * 4));
+        CK(ctx->wperm[i].ensure((size_t)n * 4)); CK(ctx->wpnode[i].ensure((size_t)n * 4)); CK(ctx->wslot[i].ensure((size_t)n + 64));
+        CK(ctx->wcpar[i].ensure((size_t)max_chunks * 4)); CK(ctx->wcstart[i].ensure((size_t)max_chunks * 4));
+        CK(ctx->wclen[i].ensure((size_t)max_chunks * 4));
+    }
+    const int n_tiles = (n + 1023) / 1024;
+    CK(ctx->p_group.ensure((size_t)n_tiles * 32 * 8 * sizeof(uint16_t)));
+    CK(ctx->p_tilecnt.ensure((size_t)n_tiles * 8 * sizeof(uint32_t)));
+    CK(ctx->p_tileoff.ensure((size_t)(n_tiles + 1) * 8 * sizeof(uint32_t)));
+    CK(ctx->p_segbase.ensure((size_t)(max_parents + 1) * 8 * sizeof(uint32_t)));
+    CK(ctx->p_seg0.ensure((size_t)(max_newseg + 1) * sizeof(int)));
+    CK(ctx->p_seg1.ensure((size_t)(max_newseg + 1) * sizeof(int)));
+    CK(ctx->p_chunkcnt.ensure((size_t)max_newseg * sizeof(int)));
+    CK(ctx->p_chunkoff.ensure((size_t)(max_newseg + 1) * sizeof(int)));
+    const size_t acc_n = kAccHdr + (size_t)level_count_h(L - 1) * kMom;
+    CK(ctx->acc.ensure(acc_n * sizeof(double)));
+    CK(ctx->t_init.ensure((size_t)t.nt * 3 * sizeof(float)));
+
+    TreeWork w[2];
+    for (int i = 0; i < 2; ++i) {
+        w[i].x = ctx->wx[i].as<float>(); w[i].y = ctx->wy[i].as<float>(); w[i].z = ctx->wz[i].as<float>();
+        w[i].perm = ctx->wperm[i].as<int>(); w[i].pnode = ctx->wpnode[i].as<int>(); w[i].slot = ctx->wslot[i].as<uint8_t>();
+        w[i].chunk_parent = ctx->wcpar[i].as<int>(); w[i].chunk_start = ctx->wcstart[i].as<int>(); w[i].chunk_len = ctx->wclen[i].as<int>();
+    }
+    PartitionScratch ps;
+    ps.group_off = ctx->p_group.as<uint16_t>(); ps.tile_cnt = ctx->p_tilecnt.as<uint32_t>(); ps.tile_off = ctx->p_tileoff.as<uint32_t>();
+    ps.seg_base = ctx->p_segbase.as<uint32_t>(); ps.seg_start = ctx->p_seg0.as<int>(); ps.new_seg_start = ctx->p_seg1.as<int>();
+    ps.chunk_cnt = ctx->p_chunkcnt.as<int>(); ps.chunk_off = ctx->p_chunkoff.as<int>();
+    int* nchunks_dev = ctx->nchunks.as<int>();
+    int* ctrl = ctx->ctrl.as<int>();
+    double* acc = ctx->acc.as<double>();
+    double* qstate = ctx->qstate.as<double>();
+
+    CK(cudaEventRecord(ctx->ev0, s));
+    CK(cudaMemcpyAsync(ctx->t_init.p, init_means, (size_t)t.nt * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    launch_tree_init(t, ctx->t_init.as<float>(), cfg->sig2, s);
+    CK(cudaMemcpyAsync(w[0].x, ctx->bx.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(w[0].y, ctx->by.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(w[0].z, ctx->bz.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    launch_iota(w[0].perm, n, s);
+    CK(cudaMemsetAsync(w[0].pnode, 0, (size_t)n * 4, s));
+    CK(cudaMemsetAsync(acc, 0, acc_n * sizeof(double), s));
+    CK(launch_root_chunks(w[0], n, ps, chunk, nchunks_dev, s));
+    ctx->launches += 3;
+
+    int cur = 0;
+    int64_t n_parents = 1;
+    const int batch = 4;      // iterations enqueued between polls of the control word (no-ops once converged)
+    for (int l = 0; l < L; ++l) {
+        CK(cudaMemsetAsync(ctrl, 0, 8 * sizeof(int), s));
+        CK(cudaMemsetAsync(qstate, 0, 4 * sizeof(double), s));
+        const int64_t cnt = level_count_h(l);
+        const int chunks_bound = (int)((n + chunk - 1) / chunk + (l == 0 ? 0 : cnt / 8));
+        const PackedComp* level_packed = t.packed + level_base_h(l);
+        bool done = false;
+        while (!done) {
+            for (int b = 0; b < batch; ++b) {
+                CK(launch_tree_estep(w[cur], t, l, acc, chunks_bound, nchunks_dev, ctrl, s));
+                r = allreduce(ctx, acc, kAccHdr + (size_t)cnt * kMom);
+                if (r != HGMM_OK) return r;
+                launch_tree_mstep(t, l, acc, (double)ctx->n_total, cfg->ld, ctrl, s);
+                ctx->launches += 2;
+                if (cfg->ll_mode == HGMM_LL_LEVEL) {
+                    launch_tree_zero_ll(acc, ctrl, s);
+                    CK(launch_level_ll(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), n, level_packed, (int)cnt, acc,
+                                       ctx->num_sms, s));
+                    ctx->launches += 2;
+                    r = allreduce(ctx, acc, 1);
+                    if (r != HGMM_OK) return r;
+                }
+                launch_tree_converge(acc, ctrl, qstate, cfg->ls, max_iters, s);
+                ctx->launches += 1;
+            }
+            CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            done = ctx->h_ctrl[0] != 0;
+        }
+        if (out_iters) out_iters[l] = ctx->h_ctrl[1];
+        if (out_q) {
+            CK(cudaMemcpyAsync(ctx->h_dbl, qstate, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            out_q[l] = ctx->h_dbl[1];
+        }
+        if (l < L - 1) {
+            CK(launch_partition(w[cur], w[1 - cur], n, (int)n_parents, ps, chunk, nchunks_dev, s));
+            ctx->launches += 7;
+            cur = 1 - cur;
+            n_parents *= 8;
+        }
+    }
+    if (out_current) {
+        CK(ctx->current.ensure((size_t)n * sizeof(int64_t)));
+        launch_tree_current(w[cur], n, L - 1, ctx->current.as<int64_t>(), s);
+        ctx->launches += 1;
+        CK(cudaMemcpyAsync(out_current, ctx->current.p, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaEventRecord(ctx->ev1, s));
+    if (out_pi) CK(cudaMemcpyAsync(out_pi, t.pi, (size_t)t.nt * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (out_mu) CK(cudaMemcpyAsync(out_mu, t.mu, (size_t)t.nt * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (out_cov) CK(cudaMemcpyAsync(out_cov, t.cov, (size_t)t.nt * 9 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms[0] = ms; ctx->last_ms[1] = ms; ctx->last_ms[2] = 0;
+    ctx->have_tree = true;
+    return HGMM_OK;
+}
+
+int hgmm_tree_set_model(hgmm_ctx* ctx, int32_t max_level, const float* pi, const float* mu, const float* cov) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!pi || !mu || !cov) FAIL(HGMM_ERR_INVALID, "null model pointer");
+    CK(cudaSetDevice(ctx->device));
+    int r = ensure_tree_model(ctx, max_level);
+    if (r != HGMM_OK) return r;
+    TreeModel& t = ctx->tm;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(t.pi, pi, (size_t)t.nt * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(t.mu, mu, (size_t)t.nt * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(t.cov, cov, (size_t)t.nt * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
+    launch_tree_pack_all(t, s);
+    ctx->launches += 1;
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    ctx->have_tree = true;
+    return HGMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// registration
+// ------------------------------------------------------------------------------------------
+int hgmm_reg_set_target(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    int r = upload_cloud(ctx, xyz, n, mem_kind, ctx->tx, ctx->ty, ctx->tz, nullptr);
+    if (r != HGMM_OK) return r;
+    ctx->nt_pts = (int)n;
+    ctx->have_target = true;
+    return HGMM_OK;
+}
+
+static int upload_Rt(hgmm_ctx* ctx, const double* rot, const double* t) {
+    for (int k = 0; k < 9; ++k) ctx->h_dbl[k] = rot[k];
+    for (int k = 0; k < 3; ++k) ctx->h_dbl[9 + k] = t[k];
+    CK(cudaMemcpyAsync(ctx->Rt.p, ctx->h_dbl, 12 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // h_dbl is reused right away by callers only after a sync; make the copy safe
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HGMM_OK;
+}
+
+int hgmm_reg_estep(hgmm_ctx* ctx, const double* rot, const double* t, float lambda_c, double* out_m0, double* out_m1,
+                   double* out_m2) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!ctx->have_tree) FAIL(HGMM_ERR_STATE, "no tree: call hgmm_fit_tree / hgmm_tree_set_model first");
+    if (!ctx->have_target) FAIL(HGMM_ERR_STATE, "no target: call hgmm_reg_set_target first");
+    if (!rot || !t) FAIL(HGMM_ERR_INVALID, "null transform");
+    CK(cudaSetDevice(ctx->device));
+    const TreeModel& tm = ctx->tm;
+    const size_t rn = (size_t)tm.nt * 10;
+    CK(ctx->racc.ensure(rn * sizeof(double)));
+    int r = upload_Rt(ctx, rot, t);
+    if (r != HGMM_OK) return r;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->ctrl.p, 0, 8 * sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->racc.p, 0, rn * sizeof(double), s));
+    CK(launch_reg_estep(ctx->tx.as<float>(), ctx->ty.as<float>(), ctx->tz.as<float>(), ctx->nt_pts, ctx->Rt.as<double>(), tm, lambda_c,
+                        ctx->racc.as<double>(), out_m2 ? 1 : 0, ctx->ctrl.as<int>(), s));
+    ctx->launches += 1;
+    r = allreduce(ctx, ctx->racc.as<double>(), rn);
+    if (r != HGMM_OK) return r;
+    std::vector<double> h(rn);
+    CK(cudaMemcpyAsync(h.data(), ctx->racc.p, rn * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < tm.nt; ++i) {
+        const double* A = h.data() + (size_t)i * 10;
+        if (out_m0) out_m0[i] = A[0];
+        if (out_m1) { out_m1[3 * i] = A[1]; out_m1[3 * i + 1] = A[2]; out_m1[3 * i + 2] = A[3]; }
+        if (out_m2) {
+            double* M = out_m2 + 9 * (size_t)i;
+            M[0] = A[4]; M[1] = M[3] = A[5]; M[2] = M[6] = A[6]; M[4] = A[7]; M[5] = M[7] = A[8]; M[8] = A[9];
+        }
+    }
+    ctx->have_racc = true;
+    return HGMM_OK;
+}
+
+int hgmm_reg_mstep(hgmm_ctx* ctx, int32_t solver, double* rot, double* t, double* out_q) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!ctx->have_racc) FAIL(HGMM_ERR_STATE, "no moments: call hgmm_reg_estep first");
+    if (!rot || !t) FAIL(HGMM_ERR_INVALID, "null transform");
+    if (solver != HGMM_SOLVER_TWIST_LSTSQ && solver != HGMM_SOLVER_PROCRUSTES) FAIL(HGMM_ERR_INVALID, "unknown solver");
+    CK(cudaSetDevice(ctx->device));
+    int r = upload_Rt(ctx, rot, t);
+    if (r != HGMM_OK) return r;
+    cudaStream_t s = ctx->stream;
+    CK(ctx->hist.ensure(8 * sizeof(double)));
+    CK(cudaMemsetAsync(ctx->ctrl.p, 0, 8 * sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->qstate.p, 0, 4 * sizeof(double), s));
+    CK(launch_reg_solve(ctx->tm, ctx->racc.as<double>(), solver, ctx->Rt.as<double>(), ctx->hist.as<double>(), ctx->qstate.as<double>(),
+                        ctx->ctrl.as<int>(), 0.f, s));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(ctx->h_dbl, ctx->Rt.p, 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_dbl + 16, ctx->qstate.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < 9; ++k) rot[k] = ctx->h_dbl[k];
+    for (int k = 0; k < 3; ++k) t[k] = ctx->h_dbl[9 + k];
+    if (out_q) *out_q = ctx->h_dbl[17];
+    if (ctx->h_ctrl[2]) FAIL(HGMM_ERR_NUMERIC, "registration solve: singular / non-positive-definite system");
+    return HGMM_OK;
+}
+
+int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, double* t, double* out_q, int32_t* out_iters,
+                       double* out_q_hist) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!cfg || !rot || !t) FAIL(HGMM_ERR_INVALID, "null config / transform");
+    if (!ctx->have_tree) FAIL(HGMM_ERR_STATE, "no tree: call hgmm_fit_tree / hgmm_tree_set_model first");
+    if (!ctx->have_target) FAIL(HGMM_ERR_STATE, "no target: call hgmm_reg_set_target first");
+    if (cfg->solver != HGMM_SOLVER_TWIST_LSTSQ && cfg->solver != HGMM_SOLVER_PROCRUSTES) FAIL(HGMM_ERR_INVALID, "unknown solver");
+    if (cfg->maxiter < 1 || cfg->maxiter > 100000) FAIL(HGMM_ERR_INVALID, "bad maxiter");
+    CK(cudaSetDevice(ctx->device));
+    const TreeModel& tm = ctx->tm;
+    const size_t rn = (size_t)tm.nt * 10;
+    CK(ctx->racc.ensure(rn * sizeof(double)));
+    CK(ctx->hist.ensure((size_t)(cfg->maxiter + 1) * sizeof(double)));
+    int r = upload_Rt(ctx, rot, t);
+    if (r != HGMM_OK) return r;
+    cudaStream_t s = ctx->stream;
+    int* ctrl = ctx->ctrl.as<int>();
+    CK(cudaMemsetAsync(ctrl, 0, 8 * sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->qstate.p, 0, 4 * sizeof(double), s));
+    CK(cudaEventRecord(ctx->ev0, s));
+    const int batch = 4;
+    int issued = 0;
+    bool done = false;
+    while (!done && issued < cfg->maxiter) {
+        for (int b = 0; b < batch && issued < cfg->maxiter; ++b, ++issued) {
+            launch_zero_doubles(ctx->racc.as<double>(), rn, ctrl, s);
+            CK(launch_reg_estep(ctx->tx.as<float>(), ctx->ty.as<float>(), ctx->tz.as<float>(), ctx->nt_pts, ctx->Rt.as<double>(), tm,
+                                cfg->lambda_c, ctx->racc.as<double>(), 0, ctrl, s));
+            r = allreduce(ctx, ctx->racc.as<double>(), rn);
+            if (r != HGMM_OK) return r;
+            CK(launch_reg_solve(tm, ctx->racc.as<double>(), cfg->solver, ctx->Rt.as<double>(), ctx->hist.as<double>(),
+                                ctx->qstate.as<double>(), ctrl, cfg->tol, s));
+            ctx->launches += 3;
+        }
+        CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        done = ctx->h_ctrl[0] != 0;
+    }
+    CK(cudaEventRecord(ctx->ev1, s));
+    const int iters = ctx->h_ctrl[1];
+    CK(cudaMemcpyAsync(ctx->h_dbl, ctx->Rt.p, 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_dbl + 16, ctx->qstate.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_q_hist && iters > 0) CK(cudaMemcpyAsync(out_q_hist, ctx->hist.p, (size_t)iters * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < 9; ++k) rot[k] = ctx->h_dbl[k];
+    for (int k = 0; k < 3; ++k) t[k] = ctx->h_dbl[9 + k];
+    if (out_q) *out_q = ctx->h_dbl[17];
+    if (out_iters) *out_iters = iters;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms[0] = ms; ctx->last_ms[1] = ms; ctx->last_ms[2] = 0;
+    ctx->have_racc = true;
+    if (ctx->h_ctrl[2]) FAIL(HGMM_ERR_NUMERIC, "registration solve: singular / non-positive-definite system");
+    return HGMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+int hgmm_fill_vbo(hgmm_ctx* ctx, float* vbo_positions, float* vbo_colors, float scene_scale, const float* rgb_points,
+                  const float* rgb_target) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!(scene_scale > 0.f)) FAIL(HGMM_ERR_INVALID, "scene_scale must be positive");
+    CK(cudaSetDevice(ctx->device));
+    const float d1[3] = {1.f, 1.f, 1.f}, d2[3] = {1.f, 1.f, 0.f};     // gmm_kernels.cu:573-574
+    const float* c1 = rgb_points ? rgb_points : d1;
+    const float* c2 = rgb_target ? rgb_target : d2;
+    launch_fill_vbo(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, 0, vbo_positions, vbo_colors, scene_scale,
+                    c1[0], c1[1], c1[2], ctx->stream);
+    ctx->launches += ctx->n > 0 ? 1 : 0;
+    if (ctx->have_target) {
+        launch_fill_vbo(ctx->tx.as<float>(), ctx->ty.as<float>(), ctx->tz.as<float>(), ctx->nt_pts, ctx->n, vbo_positions, vbo_colors,
+                        scene_scale, c2[0], c2[1], c2[2], ctx->stream);
+        ctx->launches += ctx->nt_pts > 0 ? 1 : 0;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));     // the reference syncs here too (gmm_kernels.cu:541)
+    return HGMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+int hgmm_comm_unique_id(void* out_id128) {
+    if (!out_id128) return HGMM_ERR_INVALID;
+    if (!nccl_load()) return HGMM_ERR_NCCL;
+    ncclUniqueId128 id;
+    if (g_nccl.GetUniqueId(&id) != 0) return HGMM_ERR_NCCL;
+    memcpy(out_id128, &id, 128);
+    return HGMM_OK;
+}
+
+int hgmm_comm_init(hgmm_ctx* ctx, int rank, int nranks, const void* id128) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id128) FAIL(HGMM_ERR_INVALID, "bad rank / nranks / id");
+    if (!nccl_load()) FAIL(HGMM_ERR_NCCL, g_nccl.err);
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId128 id;
+    memcpy(&id, id128, 128);
+    int r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != 0) {
+        ctx->comm = nullptr;
+        FAIL(HGMM_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    }
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return HGMM_OK;
+}
+
+int hgmm_comm_destroy(hgmm_ctx* ctx) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (ctx->comm && g_nccl.CommDestroy) {
+        cudaStreamSynchronize(ctx->stream);
+        g_nccl.CommDestroy(ctx->comm);
+    }
+    ctx->comm = nullptr;
+    ctx->nranks = 1;
+    ctx->rank = 0;
+    return HGMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+int hgmm_measure_fp32_peak(hgmm_ctx* ctx, double* out_tflops) {
+    if (!ctx || !out_tflops) return HGMM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->hist.ensure(64));
+    const int blocks = ctx->num_sms * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        CK(launch_ffma_peak(ctx->hist.as<float>(), blocks, iters, ctx->stream));
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->launches += 1;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        const double flops = (double)blocks * 256.0 * iters * 16.0 * 8.0 * 2.0;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *out_tflops = best;
+    return HGMM_OK;
+}
+
+int hgmm_last_timing(const hgmm_ctx* ctx, double* out_ms3) {
+    if (!ctx || !out_ms3) return HGMM_ERR_INVALID;
+    out_ms3[0] = ctx->last_ms[0];
+    out_ms3[1] = ctx->last_ms[1];
+    out_ms3[2] = ctx->last_ms[2];
+    return HGMM_OK;
+}
+
+}  // extern "C"

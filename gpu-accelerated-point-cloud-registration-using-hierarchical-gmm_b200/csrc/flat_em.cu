@@ -1,0 +1,569 @@
+// flat_em.cu -- fused E+M kernels of the flat (non-hierarchical) mixture, sm_100a.
+//
+// Replaces, for the flat path (paths relative to the reference checkout):
+//   expectationStep / calculateProbability      src/c++/gmm_fit/gmm_kernels.cu:96-126,278-302
+//   maximizationStep + its 6 kernels            src/c++/gmm_fit/gmm_kernels.cu:135-210,304-350
+//   estimate_log_prob / e_step / m_step         src/python/gmm_waymo/src/gmm_impl.py:53-116
+//   predict                                     src/python/gmm_waymo/src/gmm_impl.py:147-155
+//   logLikelihoodValue (level scan of the tree) src/python/hgmm/hgmm_gpu.py:107-115
+//
+// Design: one kernel per EM iteration sweeps the cloud once.
+//   phase A  thread <-> point: log2-domain density against all J components (staged in shared
+//            memory by one 1-D TMA bulk copy), running max/sum -> per-point normaliser;
+//   phase B  thread <-> component: responsibilities re-evaluated against the tile's points
+//            (broadcast LDS.128) and the 10 centred moments accumulated in registers -- no
+//            cross-thread reduction, no N x J matrix in memory;
+//   flush    once per CTA: fp64 atomics into the [J][10] moment block.
+// A single-CTA finalize kernel turns moments into parameters (fp64), re-packs them for the next
+// iteration and evaluates the stopping rule on the device.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hgmm {
+
+// ------------------------------------------------------------------------------------------
+__global__ void aos_to_soa_kernel(const float* __restrict__ xyz, int64_t n, float* __restrict__ x,
+                                  float* __restrict__ y, float* __restrict__ z) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        x[i] = xyz[3 * i + 0];
+        y[i] = xyz[3 * i + 1];
+        z[i] = xyz[3 * i + 2];
+    }
+}
+
+// rigid transform applied while converting (registration target): p' = R p + t
+__global__ void aos_to_soa_transform_kernel(const float* __restrict__ xyz, int64_t n, const double* __restrict__ Rt,
+                                            float* __restrict__ x, float* __restrict__ y, float* __restrict__ z) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double a = xyz[3 * i], b = xyz[3 * i + 1], c = xyz[3 * i + 2];
+        x[i] = (float)(Rt[0] * a + Rt[1] * b + Rt[2] * c + Rt[9]);
+        y[i] = (float)(Rt[3] * a + Rt[4] * b + Rt[5] * c + Rt[10]);
+        z[i] = (float)(Rt[6] * a + Rt[7] * b + Rt[8] * c + Rt[11]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// parameter packing
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ PackedComp pack_diag(double logw, double mx, double my, double mz, double ix, double iy,
+                                                double iz, int nlog /*3: diag, else spherical uses ix thrice*/) {
+    // gmm_impl.py:53-78: inv_cov = 1/std; precisions = inv_cov^2; log_det = sum log(inv_cov + eps)
+    PackedComp p;
+    p.mx = (float)mx; p.my = (float)my; p.mz = (float)mz;
+    p.pad0 = p.pad1 = 0.f;
+    const double h = -0.5 * 1.4426950408889634;
+    p.axx = (float)(h * ix * ix);
+    p.ayy = (float)(h * iy * iy);
+    p.azz = (float)(h * iz * iz);
+    p.axy = p.axz = p.ayz = 0.f;
+    double log_det = log(ix + 1e-8) + log(iy + 1e-8) + log(iz + 1e-8);
+    p.c2 = (float)(1.4426950408889634 * (logw + log_det - 1.5 * 1.8378770664093453));
+    return p;
+}
+
+// One thread per (padded) component: model arrays -> PackedComp.  first=1 reproduces
+// gmm_impl.py:122 (inv_cov = 1/sqrt(cov) before the loop), otherwise :134.
+__global__ void flat_pack_kernel(FlatModel m, int first) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m.Jp) return;
+    PackedComp p;
+    if (j >= m.J) {
+        p = pack_full(-INFINITY, 0, 0, 0, Sym3{1, 0, 0, 1, 0, 1}, false, 0.0);
+        m.packed[j] = p;
+        return;
+    }
+    double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
+    double w = m.weights[j];
+    if (m.flavor == HGMM_FLAVOR_PY) {
+        double iv[3];
+        for (int d = 0; d < 3; ++d) {
+            double c = (m.cov_type == HGMM_COV_SPHERICAL) ? (double)m.covs[j] : (double)m.covs[3 * j + d];
+            iv[d] = first ? 1.0 / sqrt(c) : 1.0 / (sqrt(c + 1e-6) + 1e-8);
+            if (m.cov_type == HGMM_COV_SPHERICAL) { if (d == 0) m.inv_cov[j] = (float)iv[0]; }
+            else m.inv_cov[3 * j + d] = (float)iv[d];
+        }
+        p = pack_diag(log(w + 1e-8), mx, my, mz, iv[0], iv[1], iv[2], 3);
+    } else {
+        const float* c = m.covs + 9 * j;
+        Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
+        p = pack_full(log(w), mx, my, mz, s, m.sigma_bug != 0, 0.0);
+    }
+    m.packed[j] = p;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused E+M sweep
+// ------------------------------------------------------------------------------------------
+template <int TP, int JT>
+__global__ void __launch_bounds__(256) em_flat_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                      const float* __restrict__ pz, int n,
+                                                      const PackedComp* __restrict__ packed, int J, int Jp,
+                                                      double* __restrict__ acc, const int* __restrict__ ctrl,
+                                                      float norm_eps_on) {
+    constexpr int TPH = TP / 2;
+    constexpr int KS = 256 / TPH;          // J-splits in phase A
+    static_assert(TPH >= 32 && KS >= 1, "tile too small/large");
+    if (ctrl[0]) return;                   // converged earlier: the rest of the enqueued iterations are no-ops
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PackedComp* sp = reinterpret_cast<PackedComp*>(smem_raw);
+    float4* spts = reinterpret_cast<float4*>(smem_raw + (size_t)Jp * sizeof(PackedComp));
+    float2* sms = reinterpret_cast<float2*>(spts + TP);
+    __shared__ uint64_t bar;
+    __shared__ double s_ll[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)Jp * sizeof(PackedComp);
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(sp, packed, bytes, &bar);           // TMA 1-D bulk copy of all J packed components
+    }
+
+    // phase-B ownership: comp slot c of this thread is j = ((sw + Sdiv*c) * 32 + lane)
+    const int S = Jp >> 5;
+    int Sdiv = 1;
+    while (Sdiv < S && Sdiv < 8) Sdiv <<= 1;
+    const int G = 8 / Sdiv, g = warp / Sdiv, sw = warp % Sdiv;
+    int myCnt = 0;
+#pragma unroll
+    for (int c = 0; c < JT; ++c)
+        if (sw + Sdiv * c < S) myCnt = c + 1;
+
+    float a[JT][kMom];
+#pragma unroll
+    for (int c = 0; c < JT; ++c)
+#pragma unroll
+        for (int k = 0; k < kMom; ++k) a[c][k] = 0.f;
+
+    mbar_wait(&bar, 0);
+
+    float4 q0[JT], q1[JT];
+    float2 q2[JT];
+#pragma unroll
+    for (int c = 0; c < JT; ++c) {
+        int j = (sw + Sdiv * c) * 32 + lane;
+        if (j >= Jp) j = Jp - 1;
+        const float4* s4 = reinterpret_cast<const float4*>(sp + j);
+        q0[c] = s4[0];
+        q1[c] = s4[1];
+        q2[c] = *reinterpret_cast<const float2*>(s4 + 2);
+    }
+
+    const int pp = tid % TPH, ks = tid / TPH;
+    const int Jq = Jp / KS;
+    double ll = 0.0;
+    const int nTiles = (n + TP - 1) / TP;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const int base = tile * TP;
+        // ---------------- phase A ----------------
+        {
+            const int i0 = base + pp, i1 = base + pp + TPH;
+            float x0 = 0.f, y0 = 0.f, z0 = 0.f, x1 = 0.f, y1 = 0.f, z1 = 0.f;
+            if (i0 < n) { x0 = px[i0]; y0 = py[i0]; z0 = pz[i0]; }
+            if (i1 < n) { x1 = px[i1]; y1 = py[i1]; z1 = pz[i1]; }
+            float m0 = kNegBig, s0 = 0.f, m1 = kNegBig, s1 = 0.f;
+            const float4* c4 = reinterpret_cast<const float4*>(sp + ks * Jq);
+#pragma unroll 1
+            for (int j = 0; j < Jq; j += 4) {
+                float qa[4], qb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 p0 = c4[3 * (j + u)];
+                    const float4 p1 = c4[3 * (j + u) + 1];
+                    const float2 p2 = *reinterpret_cast<const float2*>(c4 + 3 * (j + u) + 2);
+                    float dx, dy, dz;
+                    qa[u] = quad_q2(p0, p1, p2, x0, y0, z0, dx, dy, dz);
+                    qb[u] = quad_q2(p0, p1, p2, x1, y1, z1, dx, dy, dz);
+                }
+                float mn = fmaxf(fmaxf(fmaxf(qa[0], qa[1]), fmaxf(qa[2], qa[3])), m0);
+                s0 = s0 * ex2f(m0 - mn) + ((ex2f(qa[0] - mn) + ex2f(qa[1] - mn)) + (ex2f(qa[2] - mn) + ex2f(qa[3] - mn)));
+                m0 = mn;
+                mn = fmaxf(fmaxf(fmaxf(qb[0], qb[1]), fmaxf(qb[2], qb[3])), m1);
+                s1 = s1 * ex2f(m1 - mn) + ((ex2f(qb[0] - mn) + ex2f(qb[1] - mn)) + (ex2f(qb[2] - mn) + ex2f(qb[3] - mn)));
+                m1 = mn;
+            }
+            sms[ks * TP + pp] = make_float2(m0, s0);
+            sms[ks * TP + pp + TPH] = make_float2(m1, s1);
+            if (ks == 0) {
+                spts[pp] = make_float4(x0, y0, z0, 0.f);
+                spts[pp + TPH] = make_float4(x1, y1, z1, 0.f);
+            }
+        }
+        __syncthreads();
+        for (int p = tid; p < TP; p += 256) {
+            float M = kNegBig;
+#pragma unroll
+            for (int k = 0; k < KS; ++k) M = fmaxf(M, sms[k * TP + p].x);
+            float Ssum = 0.f;
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                float2 v = sms[k * TP + p];
+                Ssum += v.y * ex2f(v.x - M);
+            }
+            float lse2 = M + lg2f(Ssum);                 // -inf when every component is dead/underflowed
+            float norm2 = lse2;
+            if (norm_eps_on != 0.f) {                    // gmm_impl.py:113  log(sum exp + 1e-8)
+                float Mx = fmaxf(lse2, kLog2Eps8);
+                norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
+            }
+            const bool valid = (base + p) < n;
+            const bool finite = norm2 > kNegBig;
+            if (valid) ll += (double)(norm2 * kLn2);
+            reinterpret_cast<float*>(spts + p)[3] = (valid && finite) ? norm2 : INFINITY;   // +inf => gamma = 0
+        }
+        __syncthreads();
+        // ---------------- phase B ----------------
+#pragma unroll 2
+        for (int i = g; i < TP; i += G) {
+            const float4 P = spts[i];
+#pragma unroll
+            for (int c = 0; c < JT; ++c) {
+                if (c < myCnt) {
+                    float dx, dy, dz;
+                    const float q = quad_q2(q0[c], q1[c], q2[c], P.x, P.y, P.z, dx, dy, dz);
+                    const float gam = ex2f(q - P.w);
+                    const float gx = gam * dx, gy = gam * dy, gz = gam * dz;
+                    a[c][0] += gam;
+                    a[c][1] += gx;
+                    a[c][2] += gy;
+                    a[c][3] += gz;
+                    a[c][4] = fmaf(gx, dx, a[c][4]);
+                    a[c][5] = fmaf(gx, dy, a[c][5]);
+                    a[c][6] = fmaf(gx, dz, a[c][6]);
+                    a[c][7] = fmaf(gy, dy, a[c][7]);
+                    a[c][8] = fmaf(gy, dz, a[c][8]);
+                    a[c][9] = fmaf(gz, dz, a[c][9]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---------------- flush ----------------
+#pragma unroll
+    for (int c = 0; c < JT; ++c) {
+        const int j = (sw + Sdiv * c) * 32 + lane;
+        if (c < myCnt && j < J) {
+            double* dst = acc + kAccHdr + (size_t)j * kMom;
+#pragma unroll
+            for (int k = 0; k < kMom; ++k) atomicAdd(dst + k, (double)a[c][k]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+    if (lane == 0) s_ll[warp] = ll;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_ll[w];
+        atomicAdd(acc, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: moments -> parameters (fp64), stopping rule, re-pack.  One CTA of 1024 threads.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) flat_finalize_kernel(FlatModel m, double* __restrict__ acc, int* __restrict__ ctrl,
+                                                             double* __restrict__ ll_hist, double n_total) {
+    if (ctrl[0]) return;
+    __shared__ double red[32];
+    __shared__ double s_total;
+    const int tid = threadIdx.x;
+    double part = 0.0;
+    for (int j = tid; j < m.J; j += blockDim.x) part += acc[kAccHdr + (size_t)j * kMom];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        s_total = t;
+    }
+    __syncthreads();
+    const double total = s_total;
+
+    for (int j = tid; j < m.J; j += blockDim.x) {
+        double* A = acc + kAccHdr + (size_t)j * kMom;
+        const double M0 = A[0];
+        const double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
+        PackedComp p;
+        if (m.flavor == HGMM_FLAVOR_PY) {
+            // gmm_impl.py:81-103 with S1 = sum g x, S2 = sum g x^2 rebuilt from the centred moments
+            const double nk = M0 + 1e-8;
+            const double S1[3] = {A[1] + mx * M0, A[2] + my * M0, A[3] + mz * M0};
+            const double mu0[3] = {mx, my, mz};
+            const double M2d[3] = {A[4], A[7], A[9]};
+            double mean[3], cov[3], iv[3];
+            for (int d = 0; d < 3; ++d) {
+                mean[d] = S1[d] / nk;
+                const double S2 = M2d[d] + 2.0 * mu0[d] * A[1 + d] + mu0[d] * mu0[d] * M0;
+                cov[d] = S2 / nk - 2.0 * mean[d] * S1[d] / nk + mean[d] * mean[d] + 1e-6;
+            }
+            if (m.cov_type == HGMM_COV_SPHERICAL) {
+                const double c = (cov[0] + cov[1] + cov[2]) / 3.0;
+                cov[0] = cov[1] = cov[2] = c;
+                m.covs[j] = (float)c;
+            } else {
+                m.covs[3 * j] = (float)cov[0]; m.covs[3 * j + 1] = (float)cov[1]; m.covs[3 * j + 2] = (float)cov[2];
+            }
+            for (int d = 0; d < 3; ++d) iv[d] = 1.0 / (sqrt(cov[d] + 1e-6) + 1e-8);
+            if (m.cov_type == HGMM_COV_SPHERICAL) m.inv_cov[j] = (float)iv[0];
+            else { m.inv_cov[3 * j] = (float)iv[0]; m.inv_cov[3 * j + 1] = (float)iv[1]; m.inv_cov[3 * j + 2] = (float)iv[2]; }
+            const double w = nk / n_total;
+            m.weights[j] = (float)w;
+            m.means[3 * j] = (float)mean[0]; m.means[3 * j + 1] = (float)mean[1]; m.means[3 * j + 2] = (float)mean[2];
+            // pack from the float-rounded values the caller will see
+            p = pack_diag(log((double)(float)w + 1e-8), (float)mean[0], (float)mean[1], (float)mean[2], iv[0], iv[1], iv[2], 3);
+        } else {
+            // gmm_kernels.cu:156-210: pi = N_j / sum N_k; mu = weighted mean; Sigma centred on the NEW mu
+            if (M0 > 0.0) {
+                const double r = 1.0 / M0;
+                const double dx = A[1] * r, dy = A[2] * r, dz = A[3] * r;
+                Sym3 s{A[4] * r - dx * dx, A[5] * r - dx * dy, A[6] * r - dx * dz, A[7] * r - dy * dy, A[8] * r - dy * dz,
+                       A[9] * r - dz * dz};
+                const double w = M0 / total;
+                const float fmx = (float)(mx + dx), fmy = (float)(my + dy), fmz = (float)(mz + dz);
+                m.means[3 * j] = fmx; m.means[3 * j + 1] = fmy; m.means[3 * j + 2] = fmz;
+                float* c = m.covs + 9 * j;
+                c[0] = (float)s.xx; c[1] = c[3] = (float)s.xy; c[2] = c[6] = (float)s.xz;
+                c[4] = (float)s.yy; c[5] = c[7] = (float)s.yz; c[8] = (float)s.zz;
+                m.weights[j] = (float)w;
+                p = pack_full(log(w), fmx, fmy, fmz, s, m.sigma_bug != 0, 0.0);
+            } else {
+                // the reference divides 0/0 here; the engine retires the component instead
+                m.weights[j] = 0.f;
+                p = pack_full(-INFINITY, mx, my, mz, Sym3{1, 0, 0, 1, 0, 1}, false, 0.0);
+            }
+        }
+        m.packed[j] = p;
+#pragma unroll
+        for (int k = 0; k < kMom; ++k) A[k] = 0.0;
+    }
+    if (tid == 0) {
+        const int it = ctrl[1];
+        const double ll = (m.flavor == HGMM_FLAVOR_PY) ? acc[0] / n_total : acc[0];
+        ll_hist[it] = ll;
+        if (m.flavor == HGMM_FLAVOR_PY && it > 0 && fabs(ll - ll_hist[it - 1]) < (double)m.tol) ctrl[0] = 1;
+        ctrl[1] = it + 1;
+        acc[0] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// hard assignment / level log-likelihood scan (phase A only, components streamed through smem)
+// ------------------------------------------------------------------------------------------
+constexpr int kStage = 512;      // components per shared-memory stage (24 KB)
+
+// MODE 0: labels[i] = argmax_j q2_ij (first maximum).  MODE 1: acc[0] += sum_i ln2 * max(lse2_i, log2 1e-15).
+template <int MODE>
+__global__ void __launch_bounds__(256) scan_components_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                              const float* __restrict__ pz, int n,
+                                                              const PackedComp* __restrict__ packed, int Jp,
+                                                              int32_t* __restrict__ labels, double* __restrict__ acc) {
+    __shared__ __align__(16) PackedComp sp[kStage];
+    __shared__ uint64_t bar;
+    __shared__ double s_ll[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    double ll = 0.0;
+    const int nPairs = (n + 1) / 2;
+    // grid-stride over point pairs; every thread of the CTA runs the same number of stages
+    const int pairsPerCta = 256;
+    const int nBlocksWork = (nPairs + pairsPerCta - 1) / pairsPerCta;
+    for (int blk = blockIdx.x; blk < nBlocksWork; blk += gridDim.x) {
+        const int i0 = (blk * pairsPerCta + tid) * 2, i1 = i0 + 1;
+        float x0 = 0.f, y0 = 0.f, z0 = 0.f, x1 = 0.f, y1 = 0.f, z1 = 0.f;
+        if (i0 < n) { x0 = px[i0]; y0 = py[i0]; z0 = pz[i0]; }
+        if (i1 < n) { x1 = px[i1]; y1 = py[i1]; z1 = pz[i1]; }
+        float m0 = kNegBig, s0 = 0.f, m1 = kNegBig, s1 = 0.f;
+        int b0 = 0, b1 = 0;
+        for (int jb = 0; jb < Jp; jb += kStage) {
+            const int cnt = min(kStage, Jp - jb);      // multiple of 4 (Jp is padded to 32)
+            __syncthreads();                           // previous stage fully consumed
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)cnt * sizeof(PackedComp);
+                mbar_expect_tx(&bar, bytes);
+                bulk_g2s(sp, packed + jb, bytes, &bar);
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            const float4* c4 = reinterpret_cast<const float4*>(sp);
+#pragma unroll 1
+            for (int j = 0; j < cnt; j += 4) {
+                float qa[4], qb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 p0 = c4[3 * (j + u)];
+                    const float4 p1 = c4[3 * (j + u) + 1];
+                    const float2 p2 = *reinterpret_cast<const float2*>(c4 + 3 * (j + u) + 2);
+                    float dx, dy, dz;
+                    qa[u] = quad_q2(p0, p1, p2, x0, y0, z0, dx, dy, dz);
+                    qb[u] = quad_q2(p0, p1, p2, x1, y1, z1, dx, dy, dz);
+                }
+                if (MODE == 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (qa[u] > m0) { m0 = qa[u]; b0 = jb + j + u; }
+                        if (qb[u] > m1) { m1 = qb[u]; b1 = jb + j + u; }
+                    }
+                } else {
+                    float mn = fmaxf(fmaxf(fmaxf(qa[0], qa[1]), fmaxf(qa[2], qa[3])), m0);
+                    s0 = s0 * ex2f(m0 - mn) + ((ex2f(qa[0] - mn) + ex2f(qa[1] - mn)) + (ex2f(qa[2] - mn) + ex2f(qa[3] - mn)));
+                    m0 = mn;
+                    mn = fmaxf(fmaxf(fmaxf(qb[0], qb[1]), fmaxf(qb[2], qb[3])), m1);
+                    s1 = s1 * ex2f(m1 - mn) + ((ex2f(qb[0] - mn) + ex2f(qb[1] - mn)) + (ex2f(qb[2] - mn) + ex2f(qb[3] - mn)));
+                    m1 = mn;
+                }
+            }
+        }
+        if (MODE == 0) {
+            if (i0 < n) labels[i0] = b0;
+            if (i1 < n) labels[i1] = b1;
+        } else {
+            // hgmm_gpu.py:115  log(max(temp, eps))
+            if (i0 < n) ll += (double)(kLn2 * fmaxf(m0 + lg2f(s0), kLog2Eps15));
+            if (i1 < n) ll += (double)(kLn2 * fmaxf(m1 + lg2f(s1), kLog2Eps15));
+        }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+        if (lane == 0) s_ll[warp] = ll;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += s_ll[w];
+            atomicAdd(acc, t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 peak probe: 8 independent FFMA chains per thread
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float seed) {
+    float a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const float b = 1.0000001f, c = 1e-7f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678f) out[0] = r;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------
+
+void launch_aos_to_soa(const float* xyz, int64_t n, float* x, float* y, float* z, cudaStream_t s) {
+    if (n <= 0) return;
+    aos_to_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(xyz, n, x, y, z);
+}
+void launch_aos_to_soa_transform(const float* xyz, int64_t n, const double* Rt, float* x, float* y, float* z, cudaStream_t s) {
+    if (n <= 0) return;
+    aos_to_soa_transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(xyz, n, Rt, x, y, z);
+}
+void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s) {
+    flat_pack_kernel<<<(m.Jp + 127) / 128, 128, 0, s>>>(m, first);
+}
+void launch_flat_finalize(const FlatModel& m, double* acc, int* ctrl, double* ll_hist, double n_total, cudaStream_t s) {
+    flat_finalize_kernel<<<1, 1024, 0, s>>>(m, acc, ctrl, ll_hist, n_total);
+}
+
+template <int TP, int JT>
+static cudaError_t launch_em_flat_t(const float* x, const float* y, const float* z, int n, const FlatModel& m, double* acc,
+                                    const int* ctrl, int num_sms, cudaStream_t s) {
+    constexpr int KS = 256 / (TP / 2);
+    const size_t smem = (size_t)m.Jp * sizeof(PackedComp) + (size_t)TP * 16 + (size_t)KS * TP * 8;
+    static bool attr_done = false;
+    static size_t attr_smem = 0;
+    auto kern = em_flat_kernel<TP, JT>;
+    if (!attr_done || smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+        attr_smem = 200 * 1024;
+    }
+    const int nTiles = (n + TP - 1) / TP;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+    if (occ < 1) occ = 1;
+    int grid = nTiles < num_sms * occ ? nTiles : num_sms * occ;
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, smem, s>>>(x, y, z, n, m.packed, m.J, m.Jp, acc, ctrl, m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f);
+    return cudaGetLastError();
+}
+
+template <int TP>
+static cudaError_t launch_em_flat_tp(int JT, const float* x, const float* y, const float* z, int n, const FlatModel& m,
+                                     double* acc, const int* ctrl, int num_sms, cudaStream_t s) {
+    switch (JT) {
+        case 1: return launch_em_flat_t<TP, 1>(x, y, z, n, m, acc, ctrl, num_sms, s);
+        case 2: return launch_em_flat_t<TP, 2>(x, y, z, n, m, acc, ctrl, num_sms, s);
+        case 3: return launch_em_flat_t<TP, 3>(x, y, z, n, m, acc, ctrl, num_sms, s);
+        default: return launch_em_flat_t<TP, 4>(x, y, z, n, m, acc, ctrl, num_sms, s);
+    }
+}
+
+int flat_pick_tile(int n, int num_sms, int requested) {
+    if (requested == 64 || requested == 128 || requested == 256 || requested == 512) return requested;
+    // enough tiles for ~4 per SM, but keep tiles large when the cloud is large
+    if ((int64_t)n >= (int64_t)num_sms * 512 * 4) return 512;
+    if ((int64_t)n >= (int64_t)num_sms * 256 * 4) return 256;
+    if ((int64_t)n >= (int64_t)num_sms * 128 * 4) return 128;
+    return 64;
+}
+
+cudaError_t launch_em_flat(const float* x, const float* y, const float* z, int n, const FlatModel& m, double* acc,
+                           const int* ctrl, int num_sms, int tile_points, cudaStream_t s) {
+    const int S = m.Jp / 32;
+    const int JT = S <= 8 ? 1 : (S + 7) / 8;     // <= 4 because J <= kMaxFlatJ (1024)
+    switch (tile_points) {
+        case 64: return launch_em_flat_tp<64>(JT, x, y, z, n, m, acc, ctrl, num_sms, s);
+        case 128: return launch_em_flat_tp<128>(JT, x, y, z, n, m, acc, ctrl, num_sms, s);
+        case 256: return launch_em_flat_tp<256>(JT, x, y, z, n, m, acc, ctrl, num_sms, s);
+        default: return launch_em_flat_tp<512>(JT, x, y, z, n, m, acc, ctrl, num_sms, s);
+    }
+}
+
+cudaError_t launch_predict(const float* x, const float* y, const float* z, int n, const PackedComp* packed, int Jp,
+                           int32_t* labels, int num_sms, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    int work = ((n + 1) / 2 + 255) / 256;
+    int grid = work < num_sms * 4 ? work : num_sms * 4;
+    scan_components_kernel<0><<<grid, 256, 0, s>>>(x, y, z, n, packed, Jp, labels, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_level_ll(const float* x, const float* y, const float* z, int n, const PackedComp* packed, int Jp,
+                            double* acc, int num_sms, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    int work = ((n + 1) / 2 + 255) / 256;
+    int grid = work < num_sms * 4 ? work : num_sms * 4;
+    scan_components_kernel<1><<<grid, 256, 0, s>>>(x, y, z, n, packed, Jp, nullptr, acc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ffma_peak(float* out, int blocks, int iters, cudaStream_t s) {
+    ffma_peak_kernel<<<blocks, 256, 0, s>>>(out, iters, 0.5f);
+    return cudaGetLastError();
+}
+
+}  // namespace hgmm

@@ -1,0 +1,96 @@
+// kernels.h -- host-visible launchers of libhgmm's CUDA kernels (internal; the public ABI is include/hgmm.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/hgmm.h"
+
+namespace hgmm {
+
+struct PackedComp;
+
+constexpr int kMaxFlatJ = 1024;          // fused flat kernel keeps <= 4 components per thread in registers
+
+struct FlatModel {
+    int J, Jp;                 // components, padded to a multiple of 32
+    int cov_type, flavor, sigma_bug;
+    float tol;
+    float* means;              // [Jp,3]
+    float* covs;               // FULL [Jp,9] | DIAG [Jp,3] | SPHERICAL [Jp]
+    float* weights;            // [Jp]
+    float* inv_cov;            // PY flavour: 1/std, [Jp,3] | [Jp]
+    PackedComp* packed;        // [Jp]
+};
+
+struct TreeModel {
+    int L;                     // levels
+    int nt;                    // total nodes 8(8^L-1)/7
+    float* pi;                 // [nt]
+    float* mu;                 // [nt,3]
+    float* cov;                // [nt,9] row-major
+    float* cplx;               // [nt] lambda_min / trace (registration pruning)
+    PackedComp* packed;        // [nt]
+};
+
+// per-level work decomposition of the permuted cloud
+struct TreeWork {
+    float *x, *y, *z;          // points in current (permuted) order
+    int* perm;                 // original index of permuted point i
+    int* pnode;                // level-local index of the parent node of permuted point i
+    uint8_t* slot;             // child slot (0..7) chosen by the last E-step
+    int* chunk_parent;         // [n_chunks] level-local parent index
+    int* chunk_start;          // [n_chunks] first permuted point
+    int* chunk_len;            // [n_chunks] number of points (<= chunk_points)
+};
+
+// flat_em.cu
+void launch_aos_to_soa(const float* xyz, int64_t n, float* x, float* y, float* z, cudaStream_t s);
+void launch_aos_to_soa_transform(const float* xyz, int64_t n, const double* Rt, float* x, float* y, float* z, cudaStream_t s);
+void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s);
+void launch_flat_finalize(const FlatModel& m, double* acc, int* ctrl, double* ll_hist, double n_total, cudaStream_t s);
+int flat_pick_tile(int n, int num_sms, int requested);
+cudaError_t launch_em_flat(const float* x, const float* y, const float* z, int n, const FlatModel& m, double* acc,
+                           const int* ctrl, int num_sms, int tile_points, cudaStream_t s);
+cudaError_t launch_predict(const float* x, const float* y, const float* z, int n, const PackedComp* packed, int Jp,
+                           int32_t* labels, int num_sms, cudaStream_t s);
+cudaError_t launch_level_ll(const float* x, const float* y, const float* z, int n, const PackedComp* packed, int Jp,
+                            double* acc, int num_sms, cudaStream_t s);
+cudaError_t launch_ffma_peak(float* out, int blocks, int iters, cudaStream_t s);
+
+// tree_em.cu
+void launch_tree_init(const TreeModel& t, const float* init_means, float sig2, cudaStream_t s);
+void launch_tree_pack_all(const TreeModel& t, cudaStream_t s);
+cudaError_t launch_tree_estep(const TreeWork& w, const TreeModel& t, int level, double* acc, int n_chunks_bound,
+                              const int* n_chunks_dev, const int* ctrl, cudaStream_t s);
+void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_total, float ld, const int* ctrl, cudaStream_t s);
+void launch_tree_converge(double* acc, int* ctrl, double* qstate, float ls, int max_iters, cudaStream_t s);
+void launch_tree_zero_ll(double* acc, const int* ctrl, cudaStream_t s);
+void launch_tree_current(const TreeWork& w, int n, int level, int64_t* current, cudaStream_t s);
+void launch_iota(int* p, int n, cudaStream_t s);
+
+struct PartitionScratch {
+    uint16_t* group_off;       // [n_groups,8] exclusive offset of each 32-point group inside its 1024-point tile
+    uint32_t* tile_cnt;        // [n_tiles,8]
+    uint32_t* tile_off;        // [n_tiles+1,8] exclusive scan (last row = totals)
+    uint32_t* seg_base;        // [n_parents+1,8] prefix counts at the segment starts
+    int* seg_start;            // [n_parents+1] current segments (by parent)
+    int* new_seg_start;        // [8*n_parents+1] segments after the split
+    int* chunk_cnt;            // [8*n_parents] chunks per new segment
+    int* chunk_off;            // [8*n_parents+1] exclusive scan
+};
+// splits every parent segment 8 ways by `slot` (stable), producing the next level's ordering in `dst`
+cudaError_t launch_partition(const TreeWork& src, TreeWork& dst, int n, int n_parents, PartitionScratch& ps, int chunk_points,
+                             int* n_chunks_dev, cudaStream_t s);
+// level-0 work list: one segment [0,n)
+cudaError_t launch_root_chunks(TreeWork& w, int n, const PartitionScratch& ps, int chunk_points, int* n_chunks_dev,
+                               cudaStream_t s);
+
+// registration.cu
+cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, int n, const double* Rt, const TreeModel& t,
+                             float lambda_c, double* racc, int want_m2, const int* ctrl, cudaStream_t s);
+cudaError_t launch_reg_solve(const TreeModel& t, const double* racc, int solver, double* Rt, double* q_hist, double* qstate,
+                             int* ctrl, float tol, cudaStream_t s);
+void launch_zero_doubles(double* p, size_t n, const int* ctrl, cudaStream_t s);
+void launch_fill_vbo(const float* x, const float* y, const float* z, int64_t n, int64_t offset, float* vbo_pos, float* vbo_col,
+                     float scene_scale, float r, float g, float b, cudaStream_t s);
+
+}  // namespace hgmm

@@ -1,0 +1,419 @@
+// registration.cu -- tree registration: descent E-step + single-CTA SE(3) solves, sm_100a.
+//
+// Replaces (paths relative to the reference checkout):
+//   gmmTreeRegESTep (pure-Python per-point loop)      src/python/hgmm/hgmm_gpu.py:550-577
+//   GMMTree.maximization_step (eigh + lstsq on host)  src/python/hgmm/hgmm_gpu.py:729-752
+//   twist_mul / twist_trans / skew                    src/python/hgmm/hgmm_gpu.py:620-664
+//   svd + Procrustes use (host, ICP only)             src/c++/common/svd3.h:355-401, icp/icp_kernel.cu:697-731
+//   GMMRegistration::pointCloudRegisterGPU            src/c++/gmm_registration/gmm_reg.cu:54-56 (empty stub)
+//   kernCopyPositionsToVBO / kernCopyVelocitiesToVBO  src/c++/gmm_registration/gmm_reg_kernels.cu:3-41
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hgmm {
+
+constexpr int kRegMom = 10;     // M0, M1(3), raw M2 (xx xy xz yy yz zz) -- fp64, uncentred
+
+// ------------------------------------------------------------------------------------------
+// E-step: one thread per target point, greedy root->leaf descent
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict__ tx, const float* __restrict__ ty,
+                                                        const float* __restrict__ tz, int n, const double* __restrict__ Rt,
+                                                        const PackedComp* __restrict__ packed, const float* __restrict__ cplx,
+                                                        int L, float lambda_c, double* __restrict__ racc, int want_m2,
+                                                        const int* __restrict__ ctrl) {
+    if (ctrl[0]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x, y, z;
+    {
+        const double a = tx[i], b = ty[i], c = tz[i];      // t_target = target R^T + t  (hgmm_gpu.py:757,613-614)
+        x = (float)(Rt[0] * a + Rt[1] * b + Rt[2] * c + Rt[9]);
+        y = (float)(Rt[3] * a + Rt[4] * b + Rt[5] * c + Rt[10]);
+        z = (float)(Rt[6] * a + Rt[7] * b + Rt[8] * c + Rt[11]);
+    }
+    int j0 = 0;                                             // child(-1) = 0
+    for (int l = 0; l < L; ++l) {
+        const float4* c4 = reinterpret_cast<const float4*>(packed + j0);
+        float q[8];
+        float m = kNegBig;
+        int best = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 p0 = __ldg(c4 + 3 * k), p1 = __ldg(c4 + 3 * k + 1);
+            const float4 p2 = __ldg(c4 + 3 * k + 2);
+            float dx, dy, dz;
+            q[k] = quad_q2(p0, p1, make_float2(p2.x, p2.y), x, y, z, dx, dy, dz);
+            if (q[k] > m) { m = q[k]; best = k; }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += ex2f(q[k] - m);
+        const float lse2 = m + lg2f(s);
+        const bool alive = lse2 > kLog2Eps15;               // den > eps else gamma = zeros (:563-567)
+        const int sid = j0 + (alive ? best : 0);
+        if (cplx[sid] <= lambda_c) break;                   // :572-573, before accumulating
+        const float gam = alive ? 1.0f / s : 0.f;           // gamma of the arg-max child
+        if (gam >= 1e-15f) {                                // accumulate() guard (:457-459)
+            double* A = racc + (size_t)sid * kRegMom;
+            const double g = gam, X = x, Y = y, Z = z;
+            atomicAdd(A + 0, g);
+            atomicAdd(A + 1, g * X);
+            atomicAdd(A + 2, g * Y);
+            atomicAdd(A + 3, g * Z);
+            if (want_m2) {
+                atomicAdd(A + 4, g * X * X);
+                atomicAdd(A + 5, g * X * Y);
+                atomicAdd(A + 6, g * X * Z);
+                atomicAdd(A + 7, g * Y * Y);
+                atomicAdd(A + 8, g * Y * Z);
+                atomicAdd(A + 9, g * Z * Z);
+            }
+        }
+        j0 = (sid + 1) * 8;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// M-step solves.  One CTA; per-thread partial sums over nodes, fixed-order tree reduction.
+// ------------------------------------------------------------------------------------------
+constexpr int kSys = 28;        // H (21 upper-triangular) + g (6) + c (1)
+constexpr int kPro = 18;        // W, sum w s (3), sum w mu (3), sum w s mu^T (9), sum w |s|^2, sum w |mu|^2
+
+template <int NV>
+__device__ void block_reduce(double* v, double* sm /*[blockDim][NV]*/, int tid, int nthreads) {
+    for (int k = 0; k < NV; ++k) sm[(size_t)k * nthreads + tid] = v[k];
+    __syncthreads();
+    for (int o = nthreads >> 1; o > 0; o >>= 1) {
+        if (tid < o)
+            for (int k = 0; k < NV; ++k) sm[(size_t)k * nthreads + tid] += sm[(size_t)k * nthreads + tid + o];
+        __syncthreads();
+    }
+    for (int k = 0; k < NV; ++k) v[k] = sm[(size_t)k * nthreads];
+}
+
+__device__ void rodrigues(const double* w, double* R) {      // twist_trans (hgmm_gpu.py:646-664)
+    const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    if (th == 0.0) {
+        R[0] = R[4] = R[8] = 1.0;
+        R[1] = R[2] = R[3] = R[5] = R[6] = R[7] = 0.0;
+        return;
+    }
+    const double nx = w[0] / th, ny = w[1] / th, nz = w[2] / th;
+    const double c = cos(th), s = sin(th), oc = 1.0 - c;
+    R[0] = c + oc * nx * nx;      R[1] = oc * nx * ny - s * nz; R[2] = oc * nx * nz + s * ny;
+    R[3] = oc * ny * nx + s * nz; R[4] = c + oc * ny * ny;      R[5] = oc * ny * nz - s * nx;
+    R[6] = oc * nz * nx - s * ny; R[7] = oc * nz * ny + s * nx; R[8] = c + oc * nz * nz;
+}
+
+// (R,t) <- (dR R, dR t + dt)   (twist_mul, hgmm_gpu.py:634-644)
+__device__ void compose(const double* dR, const double* dt, double* Rt) {
+    double Rn[9], tn[3];
+    for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) Rn[3 * a + b] = dR[3 * a] * Rt[b] + dR[3 * a + 1] * Rt[3 + b] + dR[3 * a + 2] * Rt[6 + b];
+        tn[a] = dR[3 * a] * Rt[9] + dR[3 * a + 1] * Rt[10] + dR[3 * a + 2] * Rt[11] + dt[a];
+    }
+    for (int k = 0; k < 9; ++k) Rt[k] = Rn[k];
+    for (int k = 0; k < 3; ++k) Rt[9 + k] = tn[k];
+}
+
+// in-place Cholesky solve of the 6x6 SPD system; returns false when not positive definite
+__device__ bool chol6_solve(double* H /*[36]*/, double* g /*[6] in, x out*/) {
+    for (int j = 0; j < 6; ++j) {
+        double d = H[7 * j];
+        for (int k = 0; k < j; ++k) d -= H[6 * j + k] * H[6 * j + k];
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        H[7 * j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double v = H[6 * i + j];
+            for (int k = 0; k < j; ++k) v -= H[6 * i + k] * H[6 * j + k];
+            H[6 * i + j] = v / d;
+        }
+    }
+    for (int i = 0; i < 6; ++i) {
+        double v = g[i];
+        for (int k = 0; k < i; ++k) v -= H[6 * i + k] * g[k];
+        g[i] = v / H[7 * i];
+    }
+    for (int i = 5; i >= 0; --i) {
+        double v = g[i];
+        for (int k = i + 1; k < 6; ++k) v -= H[6 * k + i] * g[k];
+        g[i] = v / H[7 * i];
+    }
+    return true;
+}
+
+// Jacobi eigen-analysis of the symmetric 3x3 S (in place -> diagonal), V accumulates rotations.
+// Same structure as svd3.h jacobiEigenanlysis (:199-241) but exact Givens angles in fp64 and
+// sweeps until the off-diagonal mass is negligible instead of 4 approximate sweeps.
+__device__ void jacobi3(double S[3][3], double V[3][3]) {
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) V[a][b] = (a == b) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        const double off = S[0][1] * S[0][1] + S[0][2] * S[0][2] + S[1][2] * S[1][2];
+        const double dia = S[0][0] * S[0][0] + S[1][1] * S[1][1] + S[2][2] * S[2][2];
+        if (off <= 1e-32 * dia || off == 0.0) break;
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = (pq == 2) ? 0 : pq, q = (pq == 0) ? 1 : 2;     // (0,1) (1,2) (0,2) as svd3.h
+            if (S[p][q] == 0.0) continue;
+            const double theta = (S[q][q] - S[p][p]) / (2.0 * S[p][q]);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+            for (int k = 0; k < 3; ++k) {       // S <- S G
+                const double a = S[k][p], b = S[k][q];
+                S[k][p] = c * a - s * b;
+                S[k][q] = s * a + c * b;
+            }
+            for (int k = 0; k < 3; ++k) {       // S <- G^T S
+                const double a = S[p][k], b = S[q][k];
+                S[p][k] = c * a - s * b;
+                S[q][k] = s * a + c * b;
+            }
+            for (int k = 0; k < 3; ++k) {
+                const double a = V[k][p], b = V[k][q];
+                V[k][p] = c * a - s * b;
+                V[k][q] = s * a + c * b;
+            }
+        }
+    }
+}
+
+// SVD of A (3x3) = U diag(sig) V^T following svd3.h:355-401: V from A^T A, B = A V, sort columns by
+// norm (descending), U from Gram-Schmidt QR of B.
+__device__ void svd3(const double A[3][3], double U[3][3], double sig[3], double V[3][3]) {
+    double S[3][3];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) S[a][b] = A[0][a] * A[0][b] + A[1][a] * A[1][b] + A[2][a] * A[2][b];
+    jacobi3(S, V);
+    double B[3][3];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) B[a][b] = A[a][0] * V[0][b] + A[a][1] * V[1][b] + A[a][2] * V[2][b];
+    double nrm[3];
+    for (int b = 0; b < 3; ++b) nrm[b] = B[0][b] * B[0][b] + B[1][b] * B[1][b] + B[2][b] * B[2][b];
+    for (int pass = 0; pass < 3; ++pass) {      // sortSingularValues (svd3.h:243-270): (0,1) (0,2) (1,2)
+        const int ci = (pass == 2) ? 1 : 0, cj = (pass == 0) ? 1 : 2;
+        if (nrm[ci] < nrm[cj]) {
+            for (int k = 0; k < 3; ++k) {
+                double t = B[k][ci]; B[k][ci] = B[k][cj]; B[k][cj] = -t;     // negated swap keeps det V = +1
+                t = V[k][ci]; V[k][ci] = V[k][cj]; V[k][cj] = -t;
+            }
+            const double t = nrm[ci]; nrm[ci] = nrm[cj]; nrm[cj] = t;
+        }
+    }
+    // QR by modified Gram-Schmidt; degenerate columns completed to a right-handed frame
+    for (int b = 0; b < 3; ++b) {
+        double v[3] = {B[0][b], B[1][b], B[2][b]};
+        for (int p = 0; p < b; ++p) {
+            const double d = U[0][p] * v[0] + U[1][p] * v[1] + U[2][p] * v[2];
+            for (int k = 0; k < 3; ++k) v[k] -= d * U[k][p];
+        }
+        double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        sig[b] = n;
+        if (n > 1e-300 && (b == 0 || n > 1e-14 * sig[0])) {
+            for (int k = 0; k < 3; ++k) U[k][b] = v[k] / n;
+        } else {
+            sig[b] = 0.0;
+            if (b == 2) {       // cross product of the first two
+                U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+                U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+                U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+            } else {            // any unit vector orthogonal to the previous columns
+                double e[3] = {0, 0, 0};
+                int ax = 0;
+                if (b == 1) {
+                    const double ax0 = fabs(U[0][0]), ax1 = fabs(U[1][0]), ax2 = fabs(U[2][0]);
+                    ax = (ax0 <= ax1 && ax0 <= ax2) ? 0 : (ax1 <= ax2 ? 1 : 2);
+                }
+                e[ax] = 1.0;
+                for (int p = 0; p < b; ++p) {
+                    const double d = U[0][p] * e[0] + U[1][p] * e[1] + U[2][p] * e[2];
+                    for (int k = 0; k < 3; ++k) e[k] -= d * U[k][p];
+                }
+                n = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+                for (int k = 0; k < 3; ++k) U[k][b] = e[k] / n;
+            }
+        }
+    }
+}
+
+__device__ double det3(const double M[3][3]) {
+    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+}
+
+// ctrl: [0] done, [1] iterations, [2] numeric failure flag.  qstate: [0] previous q, [1] last q, [2] has-previous flag
+__global__ void __launch_bounds__(256) reg_solve_kernel(TreeModel t, const double* __restrict__ racc, int solver,
+                                                        double* __restrict__ Rt, double* __restrict__ q_hist,
+                                                        double* __restrict__ qstate, int* __restrict__ ctrl, float tol) {
+    if (ctrl[0]) return;
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const double f32eps = 1.1920928955078125e-07;            // np.finfo(np.float32).eps  (hgmm_gpu.py:741)
+    if (solver == HGMM_SOLVER_TWIST_LSTSQ) {
+        double v[kSys];
+        for (int k = 0; k < kSys; ++k) v[k] = 0.0;
+        for (int i = tid; i < t.nt; i += nth) {
+            const double* A = racc + (size_t)i * kRegMom;
+            const double M0 = A[0];
+            if (M0 < f32eps) continue;
+            const float* c = t.cov + 9 * i;
+            Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
+            const double det = sym3_det(s);
+            if (!(det > 0.0)) continue;                     // the reference would emit inf/NaN rows here
+            const Sym3 ad = sym3_adj(s);
+            const double r = 1.0 / det;
+            const double P[3][3] = {{ad.xx * r, ad.xy * r, ad.xz * r}, {ad.xy * r, ad.yy * r, ad.yz * r}, {ad.xz * r, ad.yz * r, ad.zz * r}};
+            const double sx = A[1] / M0, sy = A[2] / M0, sz = A[3] / M0;
+            const double rr[3] = {t.mu[3 * i] - sx, t.mu[3 * i + 1] - sy, t.mu[3 * i + 2] - sz};
+            // J = [ -[s]x | I ]  (3x6);  rows of J^T are the 6 unknowns
+            const double Jm[3][6] = {{0, sz, -sy, 1, 0, 0}, {-sz, 0, sx, 0, 1, 0}, {sy, -sx, 0, 0, 0, 1}};
+            double PJ[3][6];
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 6; ++b) PJ[a][b] = P[a][0] * Jm[0][b] + P[a][1] * Jm[1][b] + P[a][2] * Jm[2][b];
+            int k = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b) v[k++] += M0 * (Jm[0][a] * PJ[0][b] + Jm[1][a] * PJ[1][b] + Jm[2][a] * PJ[2][b]);
+            const double Pr[3] = {P[0][0] * rr[0] + P[0][1] * rr[1] + P[0][2] * rr[2], P[1][0] * rr[0] + P[1][1] * rr[1] + P[1][2] * rr[2],
+                                  P[2][0] * rr[0] + P[2][1] * rr[1] + P[2][2] * rr[2]};
+            for (int a = 0; a < 6; ++a) v[21 + a] += M0 * (Jm[0][a] * Pr[0] + Jm[1][a] * Pr[1] + Jm[2][a] * Pr[2]);
+            v[27] += M0 * (rr[0] * Pr[0] + rr[1] * Pr[1] + rr[2] * Pr[2]);
+        }
+        block_reduce<kSys>(v, sm, tid, nth);
+        if (tid == 0) {
+            double H[36], g[6], g0[6];
+            int k = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b) { H[6 * a + b] = v[k]; H[6 * b + a] = v[k]; ++k; }
+            for (int a = 0; a < 6; ++a) g[a] = g0[a] = v[21 + a];
+            double q;
+            if (chol6_solve(H, g)) {
+                q = v[27];
+                for (int a = 0; a < 6; ++a) q -= g0[a] * g[a];          // residual sum of squares = c - g^T x
+                double dR[9];
+                rodrigues(g, dR);
+                compose(dR, g + 3, Rt);
+            } else {
+                q = nan("");
+                ctrl[2] = 1;
+                ctrl[0] = 1;
+            }
+            const int it = ctrl[1];
+            q_hist[it] = q;
+            if (qstate[2] != 0.0 && fabs(q - qstate[0]) < (double)tol) ctrl[0] = 1;   // hgmm_gpu.py:765
+            qstate[0] = q;
+            qstate[1] = q;
+            qstate[2] = 1.0;
+            ctrl[1] = it + 1;
+        }
+    } else {
+        double v[kPro];
+        for (int k = 0; k < kPro; ++k) v[k] = 0.0;
+        for (int i = tid; i < t.nt; i += nth) {
+            const double* A = racc + (size_t)i * kRegMom;
+            const double w = A[0];
+            if (w < f32eps) continue;
+            const double s[3] = {A[1] / w, A[2] / w, A[3] / w};
+            const double m[3] = {t.mu[3 * i], t.mu[3 * i + 1], t.mu[3 * i + 2]};
+            v[0] += w;
+            for (int a = 0; a < 3; ++a) {
+                v[1 + a] += w * s[a];
+                v[4 + a] += w * m[a];
+                for (int b = 0; b < 3; ++b) v[7 + 3 * a + b] += w * s[a] * m[b];
+            }
+            v[16] += w * (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+            v[17] += w * (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+        }
+        block_reduce<kPro>(v, sm, tid, nth);
+        if (tid == 0) {
+            double q = nan("");
+            if (v[0] > 0.0) {
+                const double W = v[0];
+                const double sb[3] = {v[1] / W, v[2] / W, v[3] / W}, mb[3] = {v[4] / W, v[5] / W, v[6] / W};
+                double Hm[3][3];
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) Hm[a][b] = v[7 + 3 * a + b] - W * sb[a] * mb[b];    // sum w (s-sb)(m-mb)^T
+                double U[3][3], sig[3], V[3][3];
+                svd3(Hm, U, sig, V);
+                // dR = V diag(1,1,d) U^T with d = det(V U^T)  (reflection fix the reference lacks, icp_kernel.cu:718-729)
+                const double d = (det3(V) * det3(U) < 0.0) ? -1.0 : 1.0;
+                double dR[9];
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) dR[3 * a + b] = V[a][0] * U[b][0] + V[a][1] * U[b][1] + d * V[a][2] * U[b][2];
+                double dt[3];
+                for (int a = 0; a < 3; ++a) dt[a] = mb[a] - (dR[3 * a] * sb[0] + dR[3 * a + 1] * sb[1] + dR[3 * a + 2] * sb[2]);
+                // q = sum w |dR (s - sb) - (m - mb)|^2 = Sss + Smm - 2 tr(dR Hm)
+                double tr = 0.0;
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) tr += dR[3 * a + b] * Hm[b][a];
+                const double Sss = v[16] - W * (sb[0] * sb[0] + sb[1] * sb[1] + sb[2] * sb[2]);
+                const double Smm = v[17] - W * (mb[0] * mb[0] + mb[1] * mb[1] + mb[2] * mb[2]);
+                q = Sss + Smm - 2.0 * tr;
+                compose(dR, dt, Rt);
+            } else {
+                ctrl[2] = 1;
+                ctrl[0] = 1;
+            }
+            const int it = ctrl[1];
+            q_hist[it] = q;
+            if (qstate[2] != 0.0 && fabs(q - qstate[0]) < (double)tol) ctrl[0] = 1;
+            qstate[0] = q;
+            qstate[1] = q;
+            qstate[2] = 1.0;
+            ctrl[1] = it + 1;
+        }
+    }
+}
+
+__global__ void zero_doubles_kernel(double* p, size_t n, const int* ctrl) {
+    if (ctrl && ctrl[0]) return;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
+}
+
+// pos = (-x,-y,-z)/scene_scale, 1 ; colour = rgb + 0.3, 1   (gmm_kernels.cu:71-93)
+__global__ void fill_vbo_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                                int64_t n, int64_t offset, float* __restrict__ vbo_pos, float* __restrict__ vbo_col,
+                                float c_scale, float r, float g, float b) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t o = 4 * (offset + i);
+    if (vbo_pos) {
+        reinterpret_cast<float4*>(vbo_pos)[offset + i] = make_float4(x[i] * c_scale, y[i] * c_scale, z[i] * c_scale, 1.0f);
+    }
+    if (vbo_col) {
+        vbo_col[o + 0] = r + 0.3f;
+        vbo_col[o + 1] = g + 0.3f;
+        vbo_col[o + 2] = b + 0.3f;
+        vbo_col[o + 3] = 1.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, int n, const double* Rt, const TreeModel& t,
+                             float lambda_c, double* racc, int want_m2, const int* ctrl, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    reg_estep_kernel<<<(n + 255) / 256, 256, 0, s>>>(tx, ty, tz, n, Rt, t.packed, t.cplx, t.L, lambda_c, racc, want_m2, ctrl);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reg_solve(const TreeModel& t, const double* racc, int solver, double* Rt, double* q_hist, double* qstate,
+                             int* ctrl, float tol, cudaStream_t s) {
+    const int nth = 256;
+    const size_t smem = (size_t)kSys * nth * sizeof(double);
+    reg_solve_kernel<<<1, nth, smem, s>>>(t, racc, solver, Rt, q_hist, qstate, ctrl, tol);
+    return cudaGetLastError();
+}
+
+void launch_zero_doubles(double* p, size_t n, const int* ctrl, cudaStream_t s) {
+    if (n == 0) return;
+    zero_doubles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, ctrl);
+}
+
+void launch_fill_vbo(const float* x, const float* y, const float* z, int64_t n, int64_t offset, float* vbo_pos, float* vbo_col,
+                     float scene_scale, float r, float g, float b, cudaStream_t s) {
+    if (n <= 0) return;
+    fill_vbo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, z, n, offset, vbo_pos, vbo_col, -1.0f / scene_scale, r, g, b);
+}
+
+}  // namespace hgmm

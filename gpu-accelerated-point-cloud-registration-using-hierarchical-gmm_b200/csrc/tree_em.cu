@@ -1,0 +1,513 @@
+// tree_em.cu -- per-level EM of the 8-ary hierarchical mixture and the device partition, sm_100a.
+//
+// Replaces (paths relative to the reference checkout):
+//   gmmTreeEStepKernel / accumulateDevice / gaussianPdfKernel   src/python/hgmm/hgmm_gpu.py:284-358,387-411
+//   gmmtreeMStepKernel / mlEstimator                            src/python/hgmm/hgmm_gpu.py:247-277,421-426
+//   (guards follow the CPU file, the semantic authority: hgmm_cupy_cpu_working.py:99-119,162-191)
+//   parentIdx <- currentIdx hand-off                            src/python/hgmm/hgmm_gpu.py:540
+//
+// Design.  The reference leaves points in place, gathers 8 children per
+// thread by parent index and issues up to 104 contended fp32 global atomics per point.  Here the
+// cloud is physically re-ordered at every level hand-off so that the points of one parent are
+// contiguous (stable 8-way split = a radix partition on the 3 new key bits), a parent segment is
+// cut into chunks of <= chunk_points points, and ONE WARP owns a chunk: the 8 children's packed
+// parameters sit in 384 B of shared memory, each lane walks its points keeping all 8 x 10 centred
+// moments in registers, a butterfly reduce-scatter folds the warp, and 80 fp64 atomics per chunk
+// land in the level's moment block.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hgmm {
+
+// ------------------------------------------------------------------------------------------
+// complexity(cov) = lambda_min / trace  (hgmm_gpu.py:78-82), closed-form symmetric 3x3 eigenvalues
+// ------------------------------------------------------------------------------------------
+__device__ double sym3_complexity(const Sym3& s) {
+    const double tr = s.xx + s.yy + s.zz;
+    const double p1 = s.xy * s.xy + s.xz * s.xz + s.yz * s.yz;
+    double lmin;
+    if (p1 == 0.0) {
+        lmin = fmin(s.xx, fmin(s.yy, s.zz));
+    } else {
+        const double q = tr / 3.0;
+        const double a = s.xx - q, b = s.yy - q, c = s.zz - q;
+        const double p2 = a * a + b * b + c * c + 2.0 * p1;
+        const double p = sqrt(p2 / 6.0);
+        const double ip = 1.0 / p;
+        Sym3 B{a * ip, s.xy * ip, s.xz * ip, b * ip, s.yz * ip, c * ip};
+        double r = 0.5 * sym3_det(B);
+        r = fmin(1.0, fmax(-1.0, r));
+        const double phi = acos(r) / 3.0;
+        lmin = q + 2.0 * p * cos(phi + 2.0943951023931953);   // + 2 pi / 3
+    }
+    return lmin / tr;
+}
+
+__global__ void tree_init_kernel(TreeModel t, const float* __restrict__ init_means, float sig2) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= t.nt) return;
+    // hgmm_gpu.py:487-490: pi = 1/8, mu = points[idxs[i]], cov = sig2 * I
+    const float mx = init_means[3 * j], my = init_means[3 * j + 1], mz = init_means[3 * j + 2];
+    t.pi[j] = 0.125f;
+    t.mu[3 * j] = mx; t.mu[3 * j + 1] = my; t.mu[3 * j + 2] = mz;
+    float* c = t.cov + 9 * j;
+    c[0] = c[4] = c[8] = sig2;
+    c[1] = c[2] = c[3] = c[5] = c[6] = c[7] = 0.f;
+    Sym3 s{sig2, 0, 0, sig2, 0, sig2};
+    t.cplx[j] = (float)(1.0 / 3.0);
+    t.packed[j] = pack_full(log(0.125), mx, my, mz, s, false, 1e-15);
+}
+
+// pack + complexity for an externally supplied tree (hgmm_tree_set_model)
+__global__ void tree_pack_all_kernel(TreeModel t) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= t.nt) return;
+    const float* c = t.cov + 9 * j;
+    Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
+    const double w = t.pi[j];
+    t.cplx[j] = (float)sym3_complexity(s);
+    t.packed[j] = pack_full(w > 0.0 ? log(w) : -INFINITY, t.mu[3 * j], t.mu[3 * j + 1], t.mu[3 * j + 2], s, false, 1e-15);
+}
+
+// ------------------------------------------------------------------------------------------
+// E-step: one warp per chunk
+// ------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void reduce_scatter_step(float* v, int offset, bool upper) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const float keep = upper ? v[i + N / 2] : v[i];
+        const float send = upper ? v[i] : v[i + N / 2];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, offset);
+    }
+}
+
+__global__ void __launch_bounds__(256) tree_estep_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                         const float* __restrict__ pz,
+                                                         const int* __restrict__ chunk_parent,
+                                                         const int* __restrict__ chunk_start,
+                                                         const int* __restrict__ chunk_len,
+                                                         const int* __restrict__ n_chunks_dev,
+                                                         const PackedComp* __restrict__ packed_level,
+                                                         double* __restrict__ acc, uint8_t* __restrict__ slot,
+                                                         const int* __restrict__ ctrl) {
+    if (ctrl[0]) return;
+    __shared__ __align__(16) float sch[8][96];
+    __shared__ double s_ll[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = blockIdx.x * 8 + warp;
+    const int n_chunks = *n_chunks_dev;
+    double ll = 0.0;
+    if (chunk < n_chunks) {
+        const int p = chunk_parent[chunk];
+        const int start = chunk_start[chunk];
+        const int len = chunk_len[chunk];
+        {
+            const float* src = reinterpret_cast<const float*>(packed_level + 8 * (size_t)p);
+            sch[warp][lane] = src[lane];
+            sch[warp][lane + 32] = src[lane + 32];
+            sch[warp][lane + 64] = src[lane + 64];
+        }
+        __syncwarp();
+        const float4* c4 = reinterpret_cast<const float4*>(&sch[warp][0]);
+        float v[8 * kMom];
+#pragma unroll
+        for (int i = 0; i < 8 * kMom; ++i) v[i] = 0.f;
+
+        for (int r = lane; r < len; r += 32) {
+            const int i = start + r;
+            const float x = px[i], y = py[i], z = pz[i];
+            float q[8];
+            float m = kNegBig;
+            int best = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 p0 = c4[3 * k], p1 = c4[3 * k + 1];
+                const float2 p2 = *reinterpret_cast<const float2*>(c4 + 3 * k + 2);
+                float dx, dy, dz;
+                q[k] = quad_q2(p0, p1, p2, x, y, z, dx, dy, dz);
+                if (q[k] > m) { m = q[k]; best = k; }        // first maximum, like np.argmax
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += ex2f(q[k] - m);
+            const float lse2 = m + lg2f(s);
+            // hgmm_cupy_cpu_working.py:174-178: gamma = gamma/den if den > eps else zeros
+            const bool alive = lse2 > kLog2Eps15;
+            slot[i] = (uint8_t)(alive ? best : 0);
+            ll += (double)(kLn2 * fmaxf(alive ? lse2 : kLog2Eps15, kLog2Eps15));
+            if (alive) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float gam = ex2f(q[k] - lse2);
+                    gam = (gam < 1e-15f) ? 0.f : gam;         // accumulate() skips gamma < eps (:100-101)
+                    const float4 p0 = c4[3 * k];
+                    const float dx = x - p0.x, dy = y - p0.y, dz = z - p0.z;
+                    const float gx = gam * dx, gy = gam * dy, gz = gam * dz;
+                    float* a = v + k * kMom;
+                    a[0] += gam;
+                    a[1] += gx;
+                    a[2] += gy;
+                    a[3] += gz;
+                    a[4] = fmaf(gx, dx, a[4]);
+                    a[5] = fmaf(gx, dy, a[5]);
+                    a[6] = fmaf(gx, dz, a[6]);
+                    a[7] = fmaf(gy, dy, a[7]);
+                    a[8] = fmaf(gy, dz, a[8]);
+                    a[9] = fmaf(gz, dz, a[9]);
+                }
+            }
+        }
+        // butterfly reduce-scatter 80 -> 5 values per lane, then pair all-reduce
+        reduce_scatter_step<80>(v, 16, (lane & 16) != 0);
+        reduce_scatter_step<40>(v, 8, (lane & 8) != 0);
+        reduce_scatter_step<20>(v, 4, (lane & 4) != 0);
+        reduce_scatter_step<10>(v, 2, (lane & 2) != 0);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+        if ((lane & 1) == 0) {
+            const int idx0 = ((lane & 16) ? 40 : 0) + ((lane & 8) ? 20 : 0) + ((lane & 4) ? 10 : 0) + ((lane & 2) ? 5 : 0);
+            double* dst = acc + kAccHdr + (size_t)p * (8 * kMom) + idx0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+                if (v[i] != 0.f) atomicAdd(dst + i, (double)v[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+    }
+    if (lane == 0) s_ll[warp] = ll;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_ll[w];
+        if (t != 0.0) atomicAdd(acc, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// M-step: one thread per node of the level
+// ------------------------------------------------------------------------------------------
+__global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __restrict__ acc, double n_total, float ld,
+                                  const int* __restrict__ ctrl) {
+    if (ctrl[0]) return;
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= count) return;
+    const int j = lb + local;
+    double* A = acc + kAccHdr + (size_t)local * kMom;
+    const double M0 = A[0];
+    // mlEstimator (hgmm_cupy_cpu_working.py:109-119): blank node if M0 < ld
+    if (M0 >= (double)ld) {
+        const double r = 1.0 / M0;
+        const double dx = A[1] * r, dy = A[2] * r, dz = A[3] * r;
+        Sym3 s{A[4] * r - dx * dx, A[5] * r - dx * dy, A[6] * r - dx * dz, A[7] * r - dy * dy, A[8] * r - dy * dz,
+               A[9] * r - dz * dz};
+        const float fx = (float)((double)t.mu[3 * j] + dx), fy = (float)((double)t.mu[3 * j + 1] + dy),
+                    fz = (float)((double)t.mu[3 * j + 2] + dz);
+        const double w = M0 / n_total;
+        t.pi[j] = (float)w;
+        t.mu[3 * j] = fx; t.mu[3 * j + 1] = fy; t.mu[3 * j + 2] = fz;
+        float* c = t.cov + 9 * j;
+        c[0] = (float)s.xx; c[1] = c[3] = (float)s.xy; c[2] = c[6] = (float)s.xz;
+        c[4] = (float)s.yy; c[5] = c[7] = (float)s.yz; c[8] = (float)s.zz;
+        t.cplx[j] = (float)sym3_complexity(s);
+        t.packed[j] = pack_full(log(w), fx, fy, fz, s, false, 1e-15);
+    } else {
+        t.pi[j] = 0.f;
+        t.mu[3 * j] = t.mu[3 * j + 1] = t.mu[3 * j + 2] = 0.f;
+        float* c = t.cov + 9 * j;
+        c[0] = c[4] = c[8] = 1.f;
+        c[1] = c[2] = c[3] = c[5] = c[6] = c[7] = 0.f;
+        t.cplx[j] = (float)(1.0 / 3.0);
+        t.packed[j] = pack_full(-INFINITY, 0, 0, 0, Sym3{1, 0, 0, 1, 0, 1}, false, 1e-15);
+    }
+#pragma unroll
+    for (int k = 0; k < kMom; ++k) A[k] = 0.0;
+}
+
+// |q - prevQ| < ls with prevQ = 0 at level start (hgmm_gpu.py:520,533-535).  qstate: [0] prevQ, [1] last q.
+__global__ void tree_converge_kernel(double* __restrict__ acc, int* __restrict__ ctrl, double* __restrict__ qstate, float ls,
+                                     int max_iters) {
+    if (ctrl[0]) return;
+    const double q = acc[0];
+    acc[0] = 0.0;
+    const int it = ctrl[1] + 1;
+    ctrl[1] = it;
+    qstate[1] = q;
+    if (fabs(q - qstate[0]) < (double)ls || it >= max_iters) ctrl[0] = 1;
+    qstate[0] = q;
+}
+
+__global__ void tree_zero_ll_kernel(double* __restrict__ acc, const int* __restrict__ ctrl) {
+    if (ctrl[0]) return;
+    acc[0] = 0.0;
+}
+
+// current[perm[i]] = level base + 8 * parent + slot  (hgmm_gpu.py:411)
+__global__ void tree_current_kernel(const int* __restrict__ perm, const int* __restrict__ pnode,
+                                    const uint8_t* __restrict__ slot, int n, int lb, int64_t* __restrict__ current) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) current[perm[i]] = (int64_t)lb + 8 * (int64_t)pnode[i] + slot[i];
+}
+
+__global__ void iota_kernel(int* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// ------------------------------------------------------------------------------------------
+// partition: stable 8-way split of every parent segment by `slot`
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) part_count_kernel(const uint8_t* __restrict__ slot, int n,
+                                                          uint16_t* __restrict__ group_off, uint32_t* __restrict__ tile_cnt) {
+    __shared__ uint32_t cnts[32][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * 1024 + tid;
+    const int s = (i < n) ? (int)slot[i] : 255;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t b = __ballot_sync(0xffffffffu, s == k);
+        if (lane == k) mine = __popc(b);
+    }
+    if (lane < 8) cnts[warp][lane] = mine;
+    __syncthreads();
+    if (tid < 8) {
+        uint32_t run = 0;
+        for (int w = 0; w < 32; ++w) {
+            const uint32_t c = cnts[w][tid];
+            group_off[((size_t)blockIdx.x * 32 + w) * 8 + tid] = (uint16_t)run;
+            run += c;
+        }
+        tile_cnt[(size_t)blockIdx.x * 8 + tid] = run;
+    }
+}
+
+// exclusive scan of tile_cnt over tiles for each of the 8 slots; warp k owns slot k
+__global__ void __launch_bounds__(256) part_scan_kernel(const uint32_t* __restrict__ tile_cnt, int n_tiles,
+                                                        uint32_t* __restrict__ tile_off) {
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    uint32_t run = 0;
+    for (int b = 0; b < n_tiles; b += 32) {
+        const int t = b + lane;
+        const uint32_t c = (t < n_tiles) ? tile_cnt[(size_t)t * 8 + k] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (t < n_tiles) tile_off[(size_t)t * 8 + k] = run + inc - c;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) tile_off[(size_t)n_tiles * 8 + k] = run;
+}
+
+// prefix counts G_k(pos) at every segment start (one thread per (parent, slot))
+__global__ void part_parents_kernel(const uint8_t* __restrict__ slot, int n, int n_tiles, const int* __restrict__ seg_start,
+                                    int n_parents, const uint16_t* __restrict__ group_off,
+                                    const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ seg_base) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (n_parents + 1) * 8) return;
+    const int p = idx >> 3, k = idx & 7;
+    const int pos = seg_start[p];
+    uint32_t G;
+    if (pos >= n) {
+        G = tile_off[(size_t)n_tiles * 8 + k];
+    } else {
+        const int tile = pos >> 10, grp = pos >> 5, r = pos & 31;
+        G = tile_off[(size_t)tile * 8 + k] + group_off[(size_t)grp * 8 + k];
+        const uint8_t* sp = slot + (size_t)grp * 32;
+        for (int u = 0; u < r; ++u) G += (sp[u] == k) ? 1u : 0u;
+    }
+    seg_base[idx] = G;
+}
+
+__global__ void part_children_kernel(const int* __restrict__ seg_start, int n_parents, int n,
+                                     const uint32_t* __restrict__ seg_base, int* __restrict__ new_seg_start,
+                                     int* __restrict__ chunk_cnt, int chunk_points) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_parents) return;
+    int start = seg_start[p];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = (int)(seg_base[(size_t)(p + 1) * 8 + k] - seg_base[(size_t)p * 8 + k]);
+        new_seg_start[8 * p + k] = start;
+        chunk_cnt[8 * p + k] = (c + chunk_points - 1) / chunk_points;
+        start += c;
+    }
+    if (p == n_parents - 1) new_seg_start[8 * n_parents] = n;
+}
+
+__global__ void part_scatter_kernel(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sz,
+                                    const int* __restrict__ sperm, const int* __restrict__ spnode,
+                                    const uint8_t* __restrict__ slot, int n, const uint16_t* __restrict__ group_off,
+                                    const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ seg_base,
+                                    const int* __restrict__ new_seg_start, float* __restrict__ dx, float* __restrict__ dy,
+                                    float* __restrict__ dz, int* __restrict__ dperm, int* __restrict__ dpnode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int s = (i < n) ? (int)slot[i] : 255;
+    const uint32_t same = __match_any_sync(0xffffffffu, s);
+    if (i >= n) return;
+    const uint32_t rank_in_group = __popc(same & ((1u << lane) - 1u));
+    const int p = spnode[i];
+    const uint32_t G = tile_off[(size_t)(i >> 10) * 8 + s] + group_off[(size_t)(i >> 5) * 8 + s] + rank_in_group;
+    const int dest = new_seg_start[8 * p + s] + (int)(G - seg_base[(size_t)p * 8 + s]);
+    dx[dest] = sx[i];
+    dy[dest] = sy[i];
+    dz[dest] = sz[i];
+    dperm[dest] = sperm[i];
+    dpnode[dest] = 8 * p + s;
+}
+
+// exclusive scan of chunk_cnt (single CTA), total -> chunk_off[count] and *n_chunks_dev
+__global__ void __launch_bounds__(1024) chunk_scan_kernel(const int* __restrict__ chunk_cnt, int count,
+                                                          int* __restrict__ chunk_off, int* __restrict__ n_chunks_dev) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int b = 0; b < count; b += 1024) {
+        const int i = b + tid;
+        const int c = (i < count) ? chunk_cnt[i] : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_tot[lane] = w;       // inclusive over warps
+        }
+        __syncthreads();
+        const int base = carry + (warp > 0 ? warp_tot[warp - 1] : 0);
+        if (i < count) chunk_off[i] = base + inc - c;
+        __syncthreads();
+        if (tid == 0) carry += warp_tot[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        chunk_off[count] = carry;
+        *n_chunks_dev = carry;
+    }
+}
+
+__global__ void chunk_fill_kernel(const int* __restrict__ new_seg_start, const int* __restrict__ chunk_cnt,
+                                  const int* __restrict__ chunk_off, int count, int chunk_points,
+                                  int* __restrict__ chunk_parent, int* __restrict__ chunk_start, int* __restrict__ chunk_len) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= count) return;
+    const int s0 = new_seg_start[c], s1 = new_seg_start[c + 1];
+    const int o = chunk_off[c], k = chunk_cnt[c];
+    for (int q = 0; q < k; ++q) {
+        const int st = s0 + q * chunk_points;
+        chunk_parent[o + q] = c;
+        chunk_start[o + q] = st;
+        chunk_len[o + q] = min(chunk_points, s1 - st);
+    }
+}
+
+__global__ void root_chunks_kernel(int n, int chunk_points, int* __restrict__ chunk_parent, int* __restrict__ chunk_start,
+                                   int* __restrict__ chunk_len, int* __restrict__ n_chunks_dev, int* __restrict__ seg_start) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = (n + chunk_points - 1) / chunk_points;
+    if (c == 0) {
+        *n_chunks_dev = total;
+        seg_start[0] = 0;
+        seg_start[1] = n;
+    }
+    if (c >= total) return;
+    chunk_parent[c] = 0;
+    chunk_start[c] = c * chunk_points;
+    chunk_len[c] = min(chunk_points, n - c * chunk_points);
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static inline int level_base(int l) {        // 8(8^l - 1)/7
+    int64_t p = 1;
+    for (int i = 0; i < l; ++i) p *= 8;
+    return (int)(8 * (p - 1) / 7);
+}
+static inline int level_count(int l) {       // 8^(l+1)
+    int64_t p = 8;
+    for (int i = 0; i < l; ++i) p *= 8;
+    return (int)p;
+}
+
+void launch_tree_init(const TreeModel& t, const float* init_means, float sig2, cudaStream_t s) {
+    tree_init_kernel<<<(t.nt + 127) / 128, 128, 0, s>>>(t, init_means, sig2);
+}
+void launch_tree_pack_all(const TreeModel& t, cudaStream_t s) {
+    tree_pack_all_kernel<<<(t.nt + 127) / 128, 128, 0, s>>>(t);
+}
+
+cudaError_t launch_tree_estep(const TreeWork& w, const TreeModel& t, int level, double* acc, int n_chunks_bound,
+                              const int* n_chunks_dev, const int* ctrl, cudaStream_t s) {
+    if (n_chunks_bound <= 0) return cudaSuccess;
+    const int grid = (n_chunks_bound + 7) / 8;
+    tree_estep_kernel<<<grid, 256, 0, s>>>(w.x, w.y, w.z, w.chunk_parent, w.chunk_start, w.chunk_len, n_chunks_dev,
+                                           t.packed + level_base(level), acc, w.slot, ctrl);
+    return cudaGetLastError();
+}
+
+void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_total, float ld, const int* ctrl, cudaStream_t s) {
+    const int cnt = level_count(level);
+    tree_mstep_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(t, level_base(level), cnt, acc, n_total, ld, ctrl);
+}
+
+void launch_tree_converge(double* acc, int* ctrl, double* qstate, float ls, int max_iters, cudaStream_t s) {
+    tree_converge_kernel<<<1, 1, 0, s>>>(acc, ctrl, qstate, ls, max_iters);
+}
+void launch_tree_zero_ll(double* acc, const int* ctrl, cudaStream_t s) { tree_zero_ll_kernel<<<1, 1, 0, s>>>(acc, ctrl); }
+
+void launch_tree_current(const TreeWork& w, int n, int level, int64_t* current, cudaStream_t s) {
+    if (n <= 0) return;
+    tree_current_kernel<<<(n + 255) / 256, 256, 0, s>>>(w.perm, w.pnode, w.slot, n, level_base(level), current);
+}
+void launch_iota(int* p, int n, cudaStream_t s) {
+    if (n > 0) iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n);
+}
+
+cudaError_t launch_root_chunks(TreeWork& w, int n, const PartitionScratch& ps, int chunk_points, int* n_chunks_dev,
+                               cudaStream_t s) {
+    const int total = (n + chunk_points - 1) / chunk_points;
+    root_chunks_kernel<<<(total + 255) / 256 > 0 ? (total + 255) / 256 : 1, 256, 0, s>>>(
+        n, chunk_points, w.chunk_parent, w.chunk_start, w.chunk_len, n_chunks_dev, ps.seg_start);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_partition(const TreeWork& src, TreeWork& dst, int n, int n_parents, PartitionScratch& ps, int chunk_points,
+                             int* n_chunks_dev, cudaStream_t s) {
+    const int n_tiles = (n + 1023) / 1024;
+    part_count_kernel<<<n_tiles, 1024, 0, s>>>(src.slot, n, ps.group_off, ps.tile_cnt);
+    part_scan_kernel<<<1, 256, 0, s>>>(ps.tile_cnt, n_tiles, ps.tile_off);
+    part_parents_kernel<<<((n_parents + 1) * 8 + 255) / 256, 256, 0, s>>>(src.slot, n, n_tiles, ps.seg_start, n_parents,
+                                                                        ps.group_off, ps.tile_off, ps.seg_base);
+    part_children_kernel<<<(n_parents + 127) / 128, 128, 0, s>>>(ps.seg_start, n_parents, n, ps.seg_base, ps.new_seg_start,
+                                                                 ps.chunk_cnt, chunk_points);
+    part_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(src.x, src.y, src.z, src.perm, src.pnode, src.slot, n, ps.group_off,
+                                                        ps.tile_off, ps.seg_base, ps.new_seg_start, dst.x, dst.y, dst.z,
+                                                        dst.perm, dst.pnode);
+    const int count = 8 * n_parents;
+    chunk_scan_kernel<<<1, 1024, 0, s>>>(ps.chunk_cnt, count, ps.chunk_off, n_chunks_dev);
+    chunk_fill_kernel<<<(count + 127) / 128, 128, 0, s>>>(ps.new_seg_start, ps.chunk_cnt, ps.chunk_off, count, chunk_points,
+                                                          dst.chunk_parent, dst.chunk_start, dst.chunk_len);
+    // the split segments are the next level's parent segments
+    int* t = ps.seg_start;
+    ps.seg_start = ps.new_seg_start;
+    ps.new_seg_start = t;
+    return cudaGetLastError();
+}
+
+}  // namespace hgmm

@@ -1,0 +1,18 @@
+"""hgmm_b200 -- Python face of libhgmm (B200 / sm_100a hierarchical-GMM fit + registration engine).
+
+Thin ctypes wrapper that keeps the reference's Python surface:
+
+    gmm_impl : train_gmm, predict, init_gmm_params, timer          (src/python/gmm_waymo/src/gmm_impl.py)
+    gmm      : Feature, GMM_GPU, GMM_GPU_Base, GMM_CPU, GMM_CPU_Base (src/python/gmm_waymo/src/gmm.py)
+    hgmm     : buildGMMTree, GMMTree, registration_gmmtree, RigidTransformation, EstepResult, MstepResult
+                                                                     (src/python/hgmm/hgmm_gpu.py)
+    dist     : point sharding + NCCL communicator bootstrap over torch.distributed
+    engine   : Engine, the object wrapper over the C ABI (include/hgmm.h)
+
+All compute runs in the CUDA library; there is no CPU fallback and nothing here imports `oracle`.
+"""
+from ._lib import HgmmError, LIB_PATH  # noqa: F401
+from .engine import Engine  # noqa: F401
+from . import gmm_impl, gmm, hgmm, dist  # noqa: F401
+
+__all__ = ["Engine", "HgmmError", "gmm_impl", "gmm", "hgmm", "dist", "LIB_PATH"]

@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing: one process per GPU, points sharded by rank, NCCL communicator bootstrap.
+
+The reference has no distributed code.  The data path needs exactly one
+exchange per EM iteration -- an all-reduce of the O(J) sufficient statistics -- which libhgmm issues
+itself on its stream (ncclAllReduce, fp64 payload).  torch.distributed is used only as the
+bootstrap channel for the 128-byte NCCL unique id (works over gloo or nccl).
+"""
+import numpy as np
+
+
+def shard_bounds(n, rank, world):
+    """contiguous shard [lo, hi) of n points for `rank` of `world`: sizes differ by <= 1."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def shuffled_shard(points, rank, world, seed=0):
+    """the fixed seeded shuffle + contiguous shard of SURVEY.md 8d (C5): every rank computes the same
+    permutation and keeps its own slice."""
+    pts = np.asarray(points)
+    perm = np.random.default_rng(seed).permutation(pts.shape[0])
+    lo, hi = shard_bounds(pts.shape[0], rank, world)
+    return pts[perm[lo:hi]]
+
+
+def broadcast_bytes(payload, src=0):
+    """broadcast a bytes object over the default torch.distributed group (any backend)."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    n = len(payload) if dist.get_rank() == src else 0
+    ln = torch.tensor([n], dtype=torch.int64, device=dev)
+    dist.broadcast(ln, src)
+    buf = torch.zeros(int(ln.item()), dtype=torch.uint8, device=dev)
+    if dist.get_rank() == src:
+        buf.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(buf, src)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def attach_communicator(engine):
+    """create libhgmm's NCCL communicator for every rank of the default process group."""
+    import torch.distributed as dist
+    from .engine import Engine
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = Engine.comm_unique_id() if rank == 0 else b""
+    uid = broadcast_bytes(uid, 0)
+    engine.comm_init(rank, world, uid)
+    return rank, world
+
+
+def allreduce_moments_host(local_moments):
+    """host-side mirror of the engine's exchange step (sum of packed sufficient statistics over ranks);
+    used by the CPU (gloo) tests of the sharding logic and by tooling."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(local_moments, dtype=np.float64).copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.numpy()

@@ -1,0 +1,207 @@
+"""Engine: thin object wrapper over the libhgmm C ABI (one context = one device + one stream)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "is_cuda") and hasattr(x, "data_ptr") and bool(x.is_cuda)
+
+
+class Engine:
+    """Owns an `hgmm_ctx`.  `stream` may be an int cudaStream_t handle (e.g. torch.cuda.Stream().cuda_stream)."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = L.load()
+        self._ctx = C.c_void_p()
+        handle = C.c_void_p(int(stream)) if stream else None
+        rc = self._lib.hgmm_create(C.byref(self._ctx), int(device), handle)
+        if rc != L.HGMM_OK or not self._ctx:
+            raise L.HgmmError("hgmm_create failed (status %d): no usable CUDA device %d -- libhgmm has no CPU path" % (rc, device))
+        self.device = int(device)
+        self._keep = []
+        self.n_points = 0
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.hgmm_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != L.HGMM_OK:
+            msg = self._lib.hgmm_last_error(self._ctx)
+            raise L.HgmmError("%s failed (status %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.hgmm_launch_count(self._ctx))
+
+    @property
+    def total_points(self):
+        return int(self._lib.hgmm_total_points(self._ctx))
+
+    def last_timing_ms(self):
+        out = np.zeros(3)
+        self._check(self._lib.hgmm_last_timing(self._ctx, L.ptr(out)), "hgmm_last_timing")
+        return out
+
+    def measure_fp32_peak(self):
+        out = np.zeros(1)
+        self._check(self._lib.hgmm_measure_fp32_peak(self._ctx, L.ptr(out)), "hgmm_measure_fp32_peak")
+        return float(out[0])
+
+    @staticmethod
+    def _cloud_arg(points):
+        """-> (void*, n, mem_kind, keepalive). Accepts numpy [N,3] (host) or a CUDA torch tensor [N,3] fp32 contiguous."""
+        if _is_torch_cuda(points):
+            t = points
+            if t.dim() != 2 or t.shape[1] != 3 or str(t.dtype) != "torch.float32" or not t.is_contiguous():
+                raise ValueError("device clouds must be contiguous float32 [N,3]")
+            return C.c_void_p(t.data_ptr()), int(t.shape[0]), L.MEM_DEVICE, t
+        if hasattr(points, "is_pinned") and hasattr(points, "numpy"):      # CPU torch tensor (possibly pinned)
+            t = points
+            if t.dim() != 2 or t.shape[1] != 3 or str(t.dtype) != "torch.float32" or not t.is_contiguous():
+                raise ValueError("host tensors must be contiguous float32 [N,3]")
+            return C.c_void_p(t.data_ptr()), int(t.shape[0]), L.MEM_HOST, t
+        a = np.asarray(points.points if hasattr(points, "points") else points)
+        if a.ndim != 2 or a.shape[1] != 3:
+            raise ValueError("point cloud must be [N,3]")
+        a = L.f32c(a)
+        return L.ptr(a), int(a.shape[0]), L.MEM_HOST, a
+
+    # -- data --------------------------------------------------------------------------------
+    def set_points(self, points):
+        p, n, kind, keep = self._cloud_arg(points)
+        self._check(self._lib.hgmm_set_points(self._ctx, p, n, kind), "hgmm_set_points")
+        self.n_points = n
+        return self
+
+    # -- flat mixture ------------------------------------------------------------------------
+    def fit_flat(self, means, covs, weights, cov_type="full", flavor=None, max_iter=10, tol=0.0, sigma_bug=False,
+                 tile_points=0, want_outputs=True):
+        ct = L.COV_TYPES[cov_type]
+        if flavor is None:
+            flavor = L.FLAVOR_CPP if ct == L.COV_FULL else L.FLAVOR_PY
+        means = L.f32c(means)
+        J = means.shape[0]
+        ce = {L.COV_FULL: (J, 3, 3), L.COV_DIAG: (J, 3), L.COV_SPHERICAL: (J,)}[ct]
+        covs = L.f32c(covs, ce)
+        weights = L.f32c(weights, (J,))
+        cfg = L.FlatConfig(J, ct, flavor, int(max_iter), float(tol), int(bool(sigma_bug)), int(tile_points), 0)
+        o_means = np.empty((J, 3), np.float32) if want_outputs else None
+        o_covs = np.empty(ce, np.float32) if want_outputs else None
+        o_w = np.empty(J, np.float32) if want_outputs else None
+        o_inv = np.empty((J, 3) if ct == L.COV_DIAG else (J,), np.float32) if (want_outputs and flavor == L.FLAVOR_PY) else None
+        o_ll = np.zeros(max(int(max_iter), 1), np.float64)
+        o_it = np.zeros(1, np.int32)
+        rc = self._lib.hgmm_fit_flat(self._ctx, C.byref(cfg), L.ptr(means), L.ptr(covs), L.ptr(weights), L.ptr(o_means),
+                                     L.ptr(o_covs), L.ptr(o_w), L.ptr(o_inv), L.ptr(o_ll), L.ptr(o_it))
+        self._check(rc, "hgmm_fit_flat")
+        it = int(o_it[0])
+        return {"means": o_means, "covs": o_covs, "weights": o_w, "inv_cov": o_inv, "ll": o_ll[:it], "iters": it}
+
+    def predict_flat(self, points=None):
+        if points is None:
+            n = self.n_points
+            labels = np.empty(n, np.int32)
+            rc = self._lib.hgmm_predict_flat(self._ctx, None, 0, L.MEM_HOST, L.ptr(labels))
+        else:
+            p, n, kind, keep = self._cloud_arg(points)
+            labels = np.empty(n, np.int32)
+            rc = self._lib.hgmm_predict_flat(self._ctx, p, n, kind, L.ptr(labels))
+        self._check(rc, "hgmm_predict_flat")
+        return labels
+
+    # -- hierarchical mixture ----------------------------------------------------------------
+    @staticmethod
+    def tree_total_nodes(max_level):
+        return int(L.load().hgmm_tree_total_nodes(int(max_level)))
+
+    def fit_tree(self, init_means, max_level, ls=20.0, ld=1.0e-4, sig2=0.004, ll_mode="level", max_iters_per_level=10000,
+                 chunk_points=0, want_current=True, want_outputs=True):
+        nt = self.tree_total_nodes(max_level)
+        init_means = L.f32c(init_means, (nt, 3))
+        cfg = L.TreeConfig(int(max_level), L.LL_LEVEL if ll_mode == "level" else L.LL_ESTEP, float(ls), float(ld), float(sig2),
+                           int(max_iters_per_level), int(chunk_points), 0)
+        pi = np.empty(nt, np.float32) if want_outputs else None
+        mu = np.empty((nt, 3), np.float32) if want_outputs else None
+        cov = np.empty((nt, 3, 3), np.float32) if want_outputs else None
+        cur = np.empty(self.n_points, np.int64) if want_current else None
+        iters = np.zeros(max_level, np.int32)
+        q = np.zeros(max_level, np.float64)
+        rc = self._lib.hgmm_fit_tree(self._ctx, C.byref(cfg), L.ptr(init_means), L.ptr(pi), L.ptr(mu), L.ptr(cov), L.ptr(cur),
+                                     L.ptr(iters), L.ptr(q))
+        self._check(rc, "hgmm_fit_tree")
+        return {"pi": pi, "mu": mu, "cov": cov, "current": cur, "iters": iters, "q": q}
+
+    def tree_set_model(self, max_level, pi, mu, cov):
+        nt = self.tree_total_nodes(max_level)
+        pi, mu, cov = L.f32c(pi, (nt,)), L.f32c(mu, (nt, 3)), L.f32c(cov, (nt, 3, 3))
+        self._check(self._lib.hgmm_tree_set_model(self._ctx, int(max_level), L.ptr(pi), L.ptr(mu), L.ptr(cov)), "hgmm_tree_set_model")
+        self._tree_level = int(max_level)
+        return self
+
+    # -- registration ------------------------------------------------------------------------
+    def reg_set_target(self, target):
+        p, n, kind, keep = self._cloud_arg(target)
+        self._check(self._lib.hgmm_reg_set_target(self._ctx, p, n, kind), "hgmm_reg_set_target")
+        return self
+
+    def reg_estep(self, rot, t, lambda_c, nt, want_m2=True):
+        rot = np.ascontiguousarray(rot, np.float64).reshape(3, 3)
+        t = np.ascontiguousarray(t, np.float64).reshape(3)
+        m0 = np.zeros(nt)
+        m1 = np.zeros((nt, 3))
+        m2 = np.zeros((nt, 3, 3)) if want_m2 else None
+        rc = self._lib.hgmm_reg_estep(self._ctx, L.ptr(rot), L.ptr(t), float(lambda_c), L.ptr(m0), L.ptr(m1), L.ptr(m2))
+        self._check(rc, "hgmm_reg_estep")
+        return m0, m1, m2
+
+    def reg_mstep(self, rot, t, solver="twist_lstsq"):
+        rot = np.array(rot, np.float64).reshape(3, 3).copy()
+        t = np.array(t, np.float64).reshape(3).copy()
+        q = np.zeros(1)
+        rc = self._lib.hgmm_reg_mstep(self._ctx, L.SOLVERS[solver], L.ptr(rot), L.ptr(t), L.ptr(q))
+        self._check(rc, "hgmm_reg_mstep")
+        return rot, t, float(q[0])
+
+    def register_tree(self, rot=None, t=None, solver="twist_lstsq", maxiter=20, tol=1.0e-4, lambda_c=0.01):
+        rot = np.identity(3) if rot is None else np.array(rot, np.float64).reshape(3, 3).copy()
+        t = np.zeros(3) if t is None else np.array(t, np.float64).reshape(3).copy()
+        cfg = L.RegConfig(L.SOLVERS[solver], int(maxiter), float(tol), float(lambda_c))
+        q = np.zeros(1)
+        it = np.zeros(1, np.int32)
+        hist = np.zeros(int(maxiter))
+        rc = self._lib.hgmm_register_tree(self._ctx, C.byref(cfg), L.ptr(rot), L.ptr(t), L.ptr(q), L.ptr(it), L.ptr(hist))
+        self._check(rc, "hgmm_register_tree")
+        return rot, t, float(q[0]), int(it[0]), hist[:int(it[0])]
+
+    def fill_vbo(self, vbo_pos_devptr, vbo_col_devptr, scene_scale=0.1):
+        rc = self._lib.hgmm_fill_vbo(self._ctx, C.c_void_p(vbo_pos_devptr) if vbo_pos_devptr else None,
+                                     C.c_void_p(vbo_col_devptr) if vbo_col_devptr else None, float(scene_scale), None, None)
+        self._check(rc, "hgmm_fill_vbo")
+
+    # -- multi-GPU ---------------------------------------------------------------------------
+    def comm_init(self, rank, nranks, unique_id_bytes):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id_bytes))
+        self._check(self._lib.hgmm_comm_init(self._ctx, int(rank), int(nranks), C.cast(buf, C.c_void_p)), "hgmm_comm_init")
+
+    def comm_destroy(self):
+        self._check(self._lib.hgmm_comm_destroy(self._ctx), "hgmm_comm_destroy")
+
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        rc = L.load().hgmm_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc != L.HGMM_OK:
+            raise L.HgmmError("hgmm_comm_unique_id failed (status %d): NCCL not loadable" % rc)
+        return bytes(buf)

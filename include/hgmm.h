@@ -1,0 +1,174 @@
+/*
+ * hgmm.h -- C ABI of libhgmm, the B200 (sm_100a) hierarchical-GMM fit / register engine.
+ *
+ * This is the drop-in boundary for the reference's fit/register hot path.  Each entry point
+ * names the reference interface it replaces (paths relative to the reference checkout):
+ *
+ *   hgmm_set_points        scanRegistration::initSimulation  src/c++/gmm_fit/gmm_kernels.cu:544-578
+ *                          GMMRegistration::initSimulation   src/c++/gmm_registration/gmm_reg.cu:19-43
+ *   hgmm_fit_flat          GMM::solve                        src/c++/gmm_fit/gmm_kernels.cu:371-504
+ *                          train_gmm                         src/python/gmm_waymo/src/gmm_impl.py:118-145
+ *   hgmm_predict_flat      predict                           src/python/gmm_waymo/src/gmm_impl.py:147-155
+ *   hgmm_fit_tree          buildGMMTree                      src/python/hgmm/hgmm_gpu.py:466-548
+ *   hgmm_tree_set_model    GMMTree._mixingCoeff/_mean/_covar src/python/hgmm/hgmm_gpu.py:685-706
+ *   hgmm_reg_estep         gmmTreeRegESTep                   src/python/hgmm/hgmm_gpu.py:550-577
+ *   hgmm_reg_mstep         GMMTree.maximization_step         src/python/hgmm/hgmm_gpu.py:729-752
+ *   hgmm_register_tree     GMMTree.registration              src/python/hgmm/hgmm_gpu.py:754-768
+ *                          GMMRegistration::pointCloudRegisterGPU (empty stub) gmm_reg.cu:54-56
+ *   hgmm_fill_vbo          scanRegistration::copyBoidsToVBO  src/c++/gmm_fit/gmm_kernels.cu:532-542
+ *                          GMMRegistration::copyBoidsToVBO   src/c++/gmm_registration/gmm_reg.cu:45-52
+ *   hgmm_comm_*            (no reference counterpart: points sharded over ranks, one all-reduce of
+ *                           the O(J) sufficient statistics per EM iteration)
+ *
+ * Conventions: plain pointers and sizes only; every call returns HGMM_OK (0) or a negative
+ * status and never exits the process (the C++ shim in cpp/ converts status -> exit(EXIT_FAILURE)
+ * to match common/utilities.cpp:16-25).  Host arrays are caller-owned.  vec3 arrays are packed
+ * 3 x fp32 (12 B, the layout of glm::vec3); 3x3 matrices are 9 x fp32 row-major (symmetric
+ * covariances, so glm::mat3's column-major layout is byte-identical).  A context is bound to one
+ * device and one stream; calls on one context must not overlap (the reference is single-threaded).
+ */
+#ifndef HGMM_H_
+#define HGMM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGMM_OK 0
+#define HGMM_ERR_INVALID (-1)      /* bad argument */
+#define HGMM_ERR_CUDA (-2)         /* CUDA runtime error, see hgmm_last_error */
+#define HGMM_ERR_STATE (-3)        /* call order (no points / no tree yet) */
+#define HGMM_ERR_NCCL (-4)         /* NCCL unavailable or failed */
+#define HGMM_ERR_NUMERIC (-5)      /* singular system in the registration solve */
+
+#define HGMM_MEM_HOST 0
+#define HGMM_MEM_DEVICE 1
+
+/* covariance structure of the flat mixture */
+#define HGMM_COV_FULL 0
+#define HGMM_COV_DIAG 1
+#define HGMM_COV_SPHERICAL 2
+
+/* which reference variant's EM semantics the flat fit follows (SURVEY.md section 7 compat table) */
+#define HGMM_FLAVOR_CPP 0          /* gmm_kernels.cu: full cov, pi = N_j/N, no regularisation, fixed iterations */
+#define HGMM_FLAVOR_PY 1           /* gmm_impl.py: diag/spherical, +1e-8 / +1e-6 terms, tol on mean log-lik */
+
+/* level log-likelihood used for the tree's convergence test */
+#define HGMM_LL_LEVEL 0            /* reference: scan of all 8^(l+1) nodes of the level with the new parameters */
+#define HGMM_LL_ESTEP 1            /* fast: the E-step's own 8-sibling normaliser (one iteration lag) */
+
+#define HGMM_SOLVER_TWIST_LSTSQ 0  /* GMMTree.maximization_step (linearised twist least squares) */
+#define HGMM_SOLVER_PROCRUSTES 1   /* weighted Procrustes, 3x3 Jacobi SVD (svd3.h algorithm) */
+
+typedef struct hgmm_ctx hgmm_ctx;
+
+typedef struct hgmm_flat_config {
+    int32_t n_components;          /* J */
+    int32_t cov_type;              /* HGMM_COV_* */
+    int32_t flavor;                /* HGMM_FLAVOR_* */
+    int32_t max_iter;
+    float tol;                     /* PY flavour: stop when |d mean-log-lik| < tol; CPP flavour ignores it */
+    int32_t sigma_bug;             /* CPP flavour only: reproduce gmm_kernels.cu:97-103 (d^T Sigma d) */
+    int32_t tile_points;           /* 0 = auto; points per CTA tile (64,128,256,512) */
+    int32_t reserved;
+} hgmm_flat_config;
+
+typedef struct hgmm_tree_config {
+    int32_t max_level;             /* L: levels of 8,64,...,8^L nodes; n_total = 8(8^L-1)/7 */
+    int32_t ll_mode;               /* HGMM_LL_* */
+    float ls;                      /* convergence threshold on |q - prevQ| (reference: 20 GPU / 80 CPU) */
+    float ld;                      /* blank a node whose zeroth moment is < ld (reference 1e-4) */
+    float sig2;                    /* initial isotropic variance (reference 0.004 GPU / 0.00034 CPU) */
+    int32_t max_iters_per_level;   /* safety cap; the reference has none */
+    int32_t chunk_points;          /* 0 = auto; points per warp work item (multiple of 32) */
+    int32_t reserved;
+} hgmm_tree_config;
+
+typedef struct hgmm_reg_config {
+    int32_t solver;                /* HGMM_SOLVER_* */
+    int32_t maxiter;               /* reference default 20 */
+    float tol;                     /* reference default 1e-4 on |q - q_prev| */
+    float lambda_c;                /* complexity pruning threshold, reference default 0.01 */
+} hgmm_reg_config;
+
+/* ---- lifecycle ---- */
+/* device: CUDA ordinal; stream: a cudaStream_t to launch on, or NULL for a context-owned stream. */
+int hgmm_create(hgmm_ctx** out, int device, void* stream);
+int hgmm_destroy(hgmm_ctx* ctx);
+const char* hgmm_last_error(const hgmm_ctx* ctx);
+const char* hgmm_version(void);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches evidence) */
+int64_t hgmm_launch_count(const hgmm_ctx* ctx);
+
+/* ---- data ---- */
+/* The cloud the mixture is fitted to (this rank's shard when a communicator is attached). */
+int hgmm_set_points(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind);
+/* total number of points over all ranks (= n without a communicator) */
+int64_t hgmm_total_points(const hgmm_ctx* ctx);
+
+/* ---- flat mixture ---- */
+/* init_means [J,3]; init_covs: FULL [J,9] | DIAG [J,3] | SPHERICAL [J] (variances); init_weights [J].
+ * Outputs (any may be NULL): out_means [J,3], out_covs (same shape rule), out_weights [J],
+ * out_inv_cov (PY flavour: 1/std, [J,3] or [J]), out_ll [max_iter] (PY: mean log p per iteration;
+ * CPP: sum_i log p(x_i) before each M step), out_iters (iterations actually run). All host memory. */
+int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg,
+                  const float* init_means, const float* init_covs, const float* init_weights,
+                  float* out_means, float* out_covs, float* out_weights, float* out_inv_cov,
+                  double* out_ll, int32_t* out_iters);
+/* hard assignment argmax_j(log N_j(x) + log(pi_j + eps)) with the last fitted flat model;
+ * xyz NULL = the context's own points; labels [n] int32 on the host. */
+int hgmm_predict_flat(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind, int32_t* labels);
+
+/* ---- hierarchical mixture ---- */
+int64_t hgmm_tree_total_nodes(int32_t max_level);
+/* init_means [n_total,3] (the reference draws points[randint]); outputs (any may be NULL):
+ * out_pi [n_total], out_mu [n_total,3], out_cov [n_total,9], out_current [n] int64 node id of each
+ * point at the leaf level in ORIGINAL point order, out_iters [max_level], out_q [max_level] last q. */
+int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_means,
+                  float* out_pi, float* out_mu, float* out_cov, int64_t* out_current,
+                  int32_t* out_iters, double* out_q);
+/* install a tree (e.g. one fitted elsewhere) as the registration model */
+int hgmm_tree_set_model(hgmm_ctx* ctx, int32_t max_level, const float* pi, const float* mu, const float* cov);
+
+/* ---- registration against the context's tree ---- */
+/* target cloud (NOT transformed); kept on the device for the following calls */
+int hgmm_reg_set_target(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind);
+/* one E-step of the target transformed by (rot row-major [9], t [3]); outputs [n_total], [n_total,3],
+ * [n_total,9] (out_m2 may be NULL to skip second moments) */
+int hgmm_reg_estep(hgmm_ctx* ctx, const double* rot, const double* t, float lambda_c,
+                   double* out_m0, double* out_m1, double* out_m2);
+/* one M-step from the moments of the last hgmm_reg_estep: updates (rot, t) in place, returns q */
+int hgmm_reg_mstep(hgmm_ctx* ctx, int32_t solver, double* rot, double* t, double* out_q);
+/* full loop; rot/t are in/out (pass identity/zero to start); returns the FORWARD transform that
+ * maps target onto the model (the reference returns its inverse, hgmm_gpu.py:768 -- the Python
+ * wrapper inverts). out_q_hist [maxiter] may be NULL. */
+int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, double* t,
+                       double* out_q, int32_t* out_iters, double* out_q_hist);
+
+/* ---- viewer glue ---- */
+/* writes 4 floats per point: pos = (-x, -y, -z)/scene_scale, 1 ; col = rgb + 0.3, 1.
+ * src = the context's points, then the registration target if set. vbo_* are DEVICE pointers
+ * (CUDA-mapped GL buffers). */
+int hgmm_fill_vbo(hgmm_ctx* ctx, float* vbo_positions, float* vbo_colors, float scene_scale,
+                  const float* rgb_points, const float* rgb_target);
+
+/* ---- multi-GPU ---- */
+/* 128-byte NCCL unique id, created on rank 0 and distributed by the caller (torch.distributed) */
+int hgmm_comm_unique_id(void* out_id128);
+int hgmm_comm_init(hgmm_ctx* ctx, int rank, int nranks, const void* id128);
+int hgmm_comm_destroy(hgmm_ctx* ctx);
+
+/* ---- measurement helper ---- */
+/* FP32 FMA throughput of this device in TFLOP/s (register-resident FFMA loop; the non-tensor
+ * roofline denominator bench.py reports next to the HBM one) */
+int hgmm_measure_fp32_peak(hgmm_ctx* ctx, double* out_tflops);
+/* wall/device time of the kernels of the last fit/registration call, in ms (CUDA events on the
+ * context stream): [0] total, [1] E/M kernels, [2] everything else */
+int hgmm_last_timing(const hgmm_ctx* ctx, double* out_ms3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGMM_H_ */

@@ -1,0 +1,305 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
+
+Tolerance (BASELINE.json north_star): fitted mu / Sigma / pi and the recovered SE(3) within 1e-4
+relative Frobenius of the reference semantics (float64 oracle, pinned to the unmodified reference by
+oracle/make_golden.py).  Where the oracle is slow, size-independent properties are checked instead."""
+import numpy as np
+import pytest
+
+from conftest import gold, rel_fro
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+# ------------------------------------------------------------------ flat, python variant (C1)
+@pytest.mark.parametrize("cov_type", ["diag", "spherical"])
+@pytest.mark.parametrize("tag", ["sub4k_J8", "bun000_J8", "sub4k_J32"])
+def test_flat_py_matches_reference_golden(engine, bun000, cov_type, tag):
+    g = gold("flat_py_%s_%s.npz" % (cov_type, tag))
+    X = bun000[::int(g["stride"])]
+    engine.set_points(X)
+    r = engine.fit_flat(g["means0"], g["covs0"], g["weights0"], cov_type=cov_type, max_iter=10, tol=0.0)
+    assert r["iters"] == 10
+    assert rel_fro(r["means"], g["ref_means"]) < TOL
+    assert rel_fro(r["covs"], g["ref_covs"]) < TOL
+    assert rel_fro(r["weights"], g["ref_weights"]) < TOL
+    assert rel_fro(r["inv_cov"], g["ref_inv_cov"]) < TOL
+    assert rel_fro(r["ll"], g["ref_ll"]) < TOL
+    lab = engine.predict_flat()
+    assert (lab == g["ref_labels"]).mean() > 0.999
+
+
+def test_train_gmm_api_is_drop_in(engine, bun000):
+    from hgmm_b200 import gmm_impl
+    g = gold("flat_py_diag_sub4k_J8.npz")
+    X = bun000[::10]
+    inv, mu, w, cov, ll = gmm_impl.train_gmm(X, 10, 0.0, g["means0"], g["covs0"], g["weights0"], "diag", engine=engine)
+    assert rel_fro(mu, g["ref_means"]) < TOL and rel_fro(cov, g["ref_covs"]) < TOL and len(ll) == 10
+    lab = gmm_impl.predict(X, inv, mu, w, "diag", engine=engine)
+    assert (lab == g["ref_labels"]).mean() > 0.999
+
+
+def test_flat_py_tolerance_stops_early(engine, bun000):
+    from oracle import flat_gmm
+    g = gold("flat_py_diag_sub4k_J8.npz")
+    X = bun000[::10]
+    engine.set_points(X)
+    r = engine.fit_flat(g["means0"], g["covs0"], g["weights0"], cov_type="diag", max_iter=60, tol=1e-3)
+    o = flat_gmm.py_train_gmm(X, 60, 1e-3, g["means0"], g["covs0"], g["weights0"], "diag")
+    assert r["iters"] == len(o[4]) < 60
+    assert rel_fro(r["means"], o[1]) < TOL and rel_fro(r["covs"], o[3]) < TOL
+
+
+# ------------------------------------------------------------------ flat, C++ variant (C2)
+@pytest.mark.parametrize("J,stride,sig", [(8, 10, 4e-4), (100, 10, 1e-4), (800, 4, 1e-4), (800, 4, 1.0), (33, 7, 2e-4), (1024, 8, 1e-4)])
+def test_flat_full_matches_oracle(engine, bun000, J, stride, sig):
+    from oracle import flat_gmm
+    X = bun000[::stride]
+    rng = np.random.default_rng(1)
+    mu0 = X[rng.choice(len(X), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * np.float32(sig), (J, 1, 1))
+    w0 = np.full(J, 1.0 / J, np.float32)
+    engine.set_points(X)
+    r = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10)
+    ow, omu, ocov, oll = flat_gmm.cpp_fit(X, mu0, 10, sigma0_sq=np.float32(sig))
+    assert rel_fro(r["weights"], ow) < TOL
+    assert rel_fro(r["means"], omu) < TOL
+    assert rel_fro(r["covs"], ocov) < 5 * TOL if sig == 1.0 else rel_fro(r["covs"], ocov) < TOL
+    assert rel_fro(r["ll"], oll) < TOL
+    assert abs(float(r["weights"].sum()) - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("tile", [64, 128, 256, 512])
+def test_flat_full_tile_sizes_agree(engine, bun000, tile):
+    from oracle import flat_gmm
+    X = bun000[::5]
+    rng = np.random.default_rng(2)
+    J = 96
+    mu0 = X[rng.choice(len(X), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * 2e-4, (J, 1, 1))
+    engine.set_points(X)
+    r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=4, tile_points=tile)
+    ow, omu, ocov, _ = flat_gmm.cpp_fit(X, mu0, 4, sigma0_sq=np.float32(2e-4))
+    assert rel_fro(r["means"], omu) < TOL and rel_fro(r["covs"], ocov) < TOL and rel_fro(r["weights"], ow) < TOL
+
+
+def test_flat_full_sigma_bug_flag(engine, bun000):
+    from oracle import flat_gmm
+    X = bun000[::20]
+    J = 8
+    rng = np.random.default_rng(3)
+    mu0 = X[rng.choice(len(X), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32), (J, 1, 1))
+    engine.set_points(X)
+    r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=3, sigma_bug=True)
+    ow, omu, ocov, _ = flat_gmm.cpp_fit(X, mu0, 3, sigma0_sq=1.0, sigma_bug=True)
+    assert rel_fro(r["means"], omu) < TOL and rel_fro(r["covs"], ocov) < TOL
+
+
+def test_flat_full_size_properties(engine, bun000):
+    """full bun000 x J=800 (config 2): properties that need no oracle"""
+    X = bun000
+    J = 800
+    rng = np.random.default_rng(1)
+    mu0 = X[rng.choice(len(X), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J, 1, 1))
+    engine.set_points(X)
+    r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=10)
+    assert abs(float(r["weights"].astype(np.float64).sum()) - 1.0) < 1e-5
+    assert np.all(np.diff(r["ll"]) > -1e-3 * abs(r["ll"][0]))          # EM monotonicity
+    # mixture mean == data mean (first-moment conservation of any EM step)
+    mm = (r["weights"][:, None].astype(np.float64) * r["means"]).sum(0)
+    assert np.allclose(mm, X.astype(np.float64).mean(0), atol=1e-6)
+    ev = np.linalg.eigvalsh(r["covs"].astype(np.float64))
+    assert (ev > 0).all()
+    assert np.abs(r["covs"] - np.swapaxes(r["covs"], 1, 2)).max() == 0
+    # determinism of everything but atomic order: a second run agrees to fp32 noise
+    r2 = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=10)
+    assert rel_fro(r2["means"], r["means"]) < 1e-6
+
+
+def test_flat_edge_cases(engine):
+    import hgmm_b200
+    X = np.random.default_rng(0).normal(size=(5, 3)).astype(np.float32)
+    engine.set_points(X)
+    # ragged: fewer points than a tile, J not a multiple of 32, one component
+    r = engine.fit_flat(X[:1], np.eye(3, dtype=np.float32)[None], np.ones(1, np.float32), cov_type="full", max_iter=2)
+    assert np.allclose(r["means"][0], X.mean(0), atol=1e-6) and abs(r["weights"][0] - 1) < 1e-6
+    assert np.allclose(r["covs"][0], np.cov(X.T, bias=True), atol=1e-5)
+    with pytest.raises(hgmm_b200.HgmmError):
+        engine.fit_flat(np.zeros((2000, 3)), np.tile(np.eye(3), (2000, 1, 1)), np.ones(2000) / 2000, cov_type="full", max_iter=1)
+    with pytest.raises(hgmm_b200.HgmmError):
+        hgmm_b200.Engine(0).fit_flat(X[:1], np.eye(3)[None], np.ones(1), cov_type="full", max_iter=1)     # no points set
+
+
+# ------------------------------------------------------------------ tree build (C3 semantics at oracle sizes)
+@pytest.mark.parametrize("tag", ["bun600_L2", "bun1500_L2"])
+def test_tree_build_matches_reference_golden(engine, tag):
+    g = gold("tree_build_%s.npz" % tag)
+    engine.set_points(g["points"])
+    r = engine.fit_tree(g["init_means"], int(g["L"]), ls=float(g["ls"]), ld=float(g["ld"]), sig2=float(g["sig2"]), ll_mode="level")
+    assert list(r["iters"]) == list(g["oracle_iters"])
+    assert rel_fro(r["pi"], g["ref_pi"]) < TOL
+    assert rel_fro(r["mu"], g["ref_mu"]) < TOL
+    assert rel_fro(r["cov"], g["ref_cov"]) < TOL
+    assert (r["current"] == g["oracle_current"]).mean() > 0.995
+
+
+@pytest.mark.parametrize("ll_mode", ["level", "estep"])
+@pytest.mark.parametrize("L,n", [(2, 5000), (3, 20000)])
+def test_tree_build_matches_oracle(engine, L, n, ll_mode):
+    from oracle import hgmm_tree, synth
+    X = synth.bunny_like(n, seed=7)
+    init = X[hgmm_tree.reference_init_indices(L)]
+    engine.set_points(X)
+    r = engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode=ll_mode)
+    opi, omu, ocov, ocur, oit, _ = hgmm_tree.build_gmm_tree(X, L, 20.0, 1e-4, init.astype(np.float64), sig2=np.float32(4e-4),
+                                                          ll_mode=ll_mode, return_trace=True)
+    assert list(r["iters"]) == list(oit)
+    assert rel_fro(r["pi"], opi) < TOL
+    assert rel_fro(r["mu"], omu) < TOL
+    assert rel_fro(r["cov"], ocov) < 3 * TOL
+    assert (r["current"] == ocur).mean() > 0.995
+
+
+def test_tree_lidar_properties(engine):
+    """config 3 shape (100k-point synthetic LiDAR sweep, L=4): oracle-free invariants"""
+    from oracle import hgmm_tree, synth
+    X = synth.lidar_sweep(100000, seed=2024)
+    L = 4
+    init = X[hgmm_tree.reference_init_indices(L)]
+    engine.set_points(X)
+    r = engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4.0, ll_mode="estep")
+    nt = hgmm_tree.n_total(L)
+    assert r["pi"].shape == (nt,)
+    for l in range(L):
+        lb, le = hgmm_tree.level(l), hgmm_tree.level(l + 1)
+        s = float(r["pi"][lb:le].astype(np.float64).sum())
+        assert 0.98 < s <= 1.0 + 1e-5, (l, s)                 # mass only leaks through dead points/blank nodes
+    cur = r["current"]
+    lb = hgmm_tree.level(L - 1)
+    assert cur.min() >= lb and cur.max() < nt
+    # hard-assignment histogram is consistent with the soft masses of the leaf level (same order of magnitude, same support)
+    cnt = np.bincount(cur - lb, minlength=nt - lb)
+    live = r["pi"][lb:] > 0
+    assert (cnt[~live] == 0).mean() > 0.99
+    # children stay inside their parent: leaf means are closer to their own parent's mean than to a random parent
+    par = (np.arange(lb, nt) // 8) - 1
+    d_own = np.linalg.norm(r["mu"][lb:][live] - r["mu"][par][live], axis=1)
+    d_rand = np.linalg.norm(r["mu"][lb:][live] - r["mu"][np.roll(par, 777)][live], axis=1)
+    assert np.median(d_own) < 0.5 * np.median(d_rand)
+    ev = np.linalg.eigvalsh(r["cov"][lb:][live].astype(np.float64))
+    assert (ev[:, 2] > 0).all()
+
+
+def test_buildGMMTree_api_is_drop_in(engine):
+    from hgmm_b200 import hgmm
+    g = gold("tree_build_bun600_L2.npz")
+    pi, mu, cov = hgmm.buildGMMTree(g["points"], 2, 20.0, 1e-4, sig2=float(g["sig2"]), init_means=g["init_means"], engine=engine)
+    assert rel_fro(pi, g["ref_pi"]) < TOL and rel_fro(mu, g["ref_mu"]) < TOL and rel_fro(cov, g["ref_cov"]) < TOL
+
+
+# ------------------------------------------------------------------ registration (C4 semantics)
+def test_registration_steps_match_reference_golden(engine):
+    g = gold("tree_reg_bun1500_L2.npz")
+    L = int(g["L"])
+    engine.tree_set_model(L, g["pi"], g["mu"], g["cov"])
+    engine.reg_set_target(g["target"])
+    m0, m1, m2 = engine.reg_estep(np.identity(3), np.zeros(3), float(g["lambda_c"]), len(g["pi"]))
+    assert rel_fro(m0, g["ref_M0"]) < TOL
+    assert rel_fro(m1, g["ref_M1"]) < TOL
+    rot, t, q = engine.reg_mstep(np.identity(3), np.zeros(3), "twist_lstsq")
+    assert rel_fro(rot, g["ref_step_rot"]) < TOL
+    assert rel_fro(t, g["ref_step_t"]) < 10 * TOL
+    assert abs(q - float(g["ref_step_q"][0])) < 1e-3 * abs(float(g["ref_step_q"][0]))
+
+
+def test_registration_loop_matches_reference_golden(engine):
+    g = gold("tree_reg_bun1500_L2.npz")
+    L = int(g["L"])
+    engine.tree_set_model(L, g["pi"], g["mu"], g["cov"])
+    engine.reg_set_target(g["target"])
+    rot, t, q, it, hist = engine.register_tree(solver="twist_lstsq", maxiter=20, tol=1e-4, lambda_c=float(g["lambda_c"]))
+    inv = np.c_[rot.T, -rot.T @ t]
+    ref = np.c_[g["ref_rot"], g["ref_t"]]
+    assert rel_fro(inv, ref) < TOL
+    assert abs(it - int(g["oracle_iters"])) <= 1
+
+
+def test_registration_gmmtree_api(engine):
+    from hgmm_b200 import hgmm
+    g = gold("tree_reg_bun1500_L2.npz")
+    gt = hgmm.GMMTree(None, tree_level=int(g["L"]), lambda_c=float(g["lambda_c"]), engine=engine)
+    gt.set_model(g["pi"], g["mu"], g["cov"])
+    res = gt.registration(g["target"], 20, 1e-4)
+    assert rel_fro(res.transformation.rot, g["ref_rot"]) < TOL and rel_fro(res.transformation.t, g["ref_t"]) < 10 * TOL
+    est = gt.expectation_step(g["target"])
+    assert rel_fro(est.momentZero, g["ref_M0"]) < TOL
+    ms = gt.maximization_step(est, hgmm.RigidTransformation())
+    assert rel_fro(ms.transformation.rot, g["ref_step_rot"]) < TOL
+
+
+def test_registration_procrustes_matches_oracle(engine):
+    from oracle import registration as oreg
+    g = gold("tree_reg_bun1500_L2.npz")
+    L = int(g["L"])
+    engine.tree_set_model(L, g["pi"], g["mu"], g["cov"])
+    engine.reg_set_target(g["target"])
+    m0, m1, _ = engine.reg_estep(np.identity(3), np.zeros(3), float(g["lambda_c"]), len(g["pi"]), want_m2=False)
+    rot, t, q = engine.reg_mstep(np.identity(3), np.zeros(3), "procrustes_svd")
+    oR, ot, oq = oreg.reg_m_step_procrustes(m0, m1, g["mu"].astype(np.float32).astype(np.float64), np.identity(3), np.zeros(3))
+    assert rel_fro(rot, oR) < TOL and np.abs(t - ot).max() < 1e-6
+    assert abs(q - oq) < 1e-6 * max(abs(oq), 1e-12) + 1e-12
+    assert abs(np.linalg.det(rot) - 1.0) < 1e-9 and np.abs(rot @ rot.T - np.identity(3)).max() < 1e-9
+    rot, t, q, it, _ = engine.register_tree(solver="procrustes_svd", maxiter=30, tol=1e-9)
+    inv = rot.T
+    assert rel_fro(inv, g["true_rot"].T) < 5e-2 or rel_fro(rot, g["true_rot"].T) < 5e-2
+
+
+def test_bunny_registration_recovers_ground_truth(engine, bun000, bun045):
+    """config 4: bun000 -> bun045 against data/bun.conf's pose (34.3 deg about y); accuracy anchor, not parity.
+    The tree is built on bun000 (source); registering bun045 returns the source->target transform."""
+    from oracle import hgmm_tree
+    q = np.array([0.00548449, -0.294635, -0.0038555, 0.955586])     # x y z w, data/bun.conf:3
+    x, y, z, w = q
+    Rq = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                   [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                   [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    tq = np.array([-0.0520211, -0.000383981, -0.0109223])
+    # p_bun000frame = Rq^T p_bun045 + tq     -> maps target(bun045) onto the model(bun000)
+    L = 3
+    init = bun000[hgmm_tree.reference_init_indices(L)]
+    engine.set_points(bun000)
+    engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep")
+    engine.reg_set_target(bun045)
+    # start from a coarse guess (25 deg about y): GMM-tree registration is local
+    th = np.deg2rad(-25.0)
+    R0 = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+    rot, t, qq, it, _ = engine.register_tree(rot=R0, t=np.zeros(3), solver="twist_lstsq", maxiter=60, tol=1e-6, lambda_c=0.01)
+    ang = np.rad2deg(np.arccos(np.clip((np.trace(rot @ Rq) - 1) / 2, -1, 1)))      # rot ~ Rq^T
+    assert ang < 3.0, ang
+    assert np.linalg.norm(t - tq) < 0.01
+
+
+def test_fill_vbo(engine):
+    import torch
+    X = np.arange(30, dtype=np.float32).reshape(10, 3)
+    engine.set_points(X)
+    engine.reg_set_target(X[:4] + 100)
+    pos = torch.zeros(14 * 4, device="cuda")
+    col = torch.zeros(14 * 4, device="cuda")
+    engine.fill_vbo(pos.data_ptr(), col.data_ptr(), 0.1)
+    p = pos.cpu().numpy().reshape(14, 4)
+    c = col.cpu().numpy().reshape(14, 4)
+    assert np.allclose(p[:10, :3], -X / 0.1) and np.allclose(p[10:, :3], -(X[:4] + 100) / 0.1) and (p[:, 3] == 1).all()
+    assert np.allclose(c[:10], [1.3, 1.3, 1.3, 1.0]) and np.allclose(c[10:], [1.3, 1.3, 0.3, 1.0])
+
+
+def test_device_resident_input(engine, bun000):
+    import torch
+    Xd = torch.from_numpy(bun000[::10]).cuda()
+    g = gold("flat_py_diag_sub4k_J8.npz")
+    engine.set_points(Xd)
+    r = engine.fit_flat(g["means0"], g["covs0"], g["weights0"], cov_type="diag", max_iter=10)
+    assert rel_fro(r["means"], g["ref_means"]) < TOL

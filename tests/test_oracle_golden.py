@@ -1,0 +1,94 @@
+"""CPU: the oracle against the committed golden vectors (outputs of the UNMODIFIED reference run in
+the build container by oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import gold, rel_fro
+from oracle import flat_gmm, hgmm_tree, registration as oreg
+
+
+@pytest.mark.parametrize("cov_type", ["diag", "spherical"])
+@pytest.mark.parametrize("tag", ["sub4k_J8", "bun000_J8", "sub4k_J32"])
+def test_flat_py_matches_reference(bun000, cov_type, tag):
+    g = gold("flat_py_%s_%s.npz" % (cov_type, tag))
+    X = bun000[::int(g["stride"])]
+    inv, mu, w, cov, ll = flat_gmm.py_train_gmm(X, 10, 0.0, g["means0"], g["covs0"], g["weights0"], cov_type)
+    assert rel_fro(mu, g["ref_means"]) < 1e-10
+    assert rel_fro(cov, g["ref_covs"]) < 1e-10
+    assert rel_fro(w, g["ref_weights"]) < 1e-10
+    assert rel_fro(inv, g["ref_inv_cov"]) < 1e-10
+    assert rel_fro(ll, g["ref_ll"]) < 1e-7          # reference rounds log(2 pi) to fp32
+    lab = flat_gmm.py_predict(X.astype(np.float64), inv, mu, w, cov_type)
+    assert (lab == g["ref_labels"]).all()
+    # the reference's own float32 run sits within ~1e-3 of its float64 self
+    assert rel_fro(g["ref32_means"], g["ref_means"]) < 2e-3
+
+
+@pytest.mark.parametrize("tag", ["bun600_L2", "bun1500_L2"])
+def test_tree_build_matches_reference(tag):
+    g = gold("tree_build_%s.npz" % tag)
+    pi, mu, cov, cur, iters, _ = hgmm_tree.build_gmm_tree(g["points"], int(g["L"]), float(g["ls"]), float(g["ld"]), g["init_means"],
+                                                          sig2=float(g["sig2"]), ll_mode="level", return_trace=True)
+    assert rel_fro(pi, g["ref_pi"]) < 1e-9
+    assert rel_fro(mu, g["ref_mu"]) < 1e-9
+    assert rel_fro(cov, g["ref_cov"]) < 1e-9
+    assert list(iters) == list(g["oracle_iters"])
+    assert (cur == g["oracle_current"]).all()
+
+
+def test_tree_init_indices_reproduce_reference_rng():
+    idx = hgmm_tree.reference_init_indices(2, flavor="gpu")
+    rs = np.random.RandomState(72)
+    assert (idx == rs.randint(72, size=72)).all()
+    assert hgmm_tree.n_total(4) == 4680 and hgmm_tree.level(3) == 584 and hgmm_tree.n_total(5) == 37448
+
+
+def test_registration_matches_reference():
+    g = gold("tree_reg_bun1500_L2.npz")
+    L = int(g["L"])
+    M0, M1, M2 = oreg.reg_e_step(g["target"], g["pi"], g["mu"], g["cov"], L, float(g["lambda_c"]))
+    assert rel_fro(M0, g["ref_M0"]) < 1e-12
+    assert rel_fro(M1, g["ref_M1"]) < 1e-12
+    R, t, q, x = oreg.reg_m_step_lstsq(M0, M1, g["pi"], g["mu"], g["cov"], np.identity(3), np.zeros(3))
+    assert rel_fro(R, g["ref_step_rot"]) < 1e-10 and rel_fro(t, g["ref_step_t"]) < 1e-10
+    assert rel_fro(q, g["ref_step_q"]) < 1e-10
+    H, gg, c = oreg.reg_normal_equations(M0, M1, g["mu"], g["cov"])
+    xn = np.linalg.solve(H, gg)
+    assert rel_fro(xn, x) < 1e-7
+    assert abs((c - gg @ xn) - float(q[0])) < 1e-6 * abs(float(q[0]))
+    fR, ft, fq, it = oreg.registration(g["target"], g["pi"], g["mu"], g["cov"], L, float(g["lambda_c"]), 20, 1e-4)
+    assert rel_fro(fR, g["ref_rot"]) < 1e-9 and rel_fro(ft, g["ref_t"]) < 1e-9
+    assert it == int(g["oracle_iters"])
+    # and it actually registers: the recovered rotation is the applied 8 degrees about z
+    assert rel_fro(fR, g["true_rot"]) < 3e-2
+
+
+def test_procrustes_oracle_recovers_known_transform():
+    rng = np.random.default_rng(5)
+    mu = rng.normal(size=(50, 3))
+    w = rng.uniform(0.5, 2.0, 50)
+    th = 0.3
+    R = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+    t = np.array([0.1, -0.2, 0.05])
+    s = (mu - t) @ R          # R s + t = mu
+    r2, t2, q = oreg.reg_m_step_procrustes(w, w[:, None] * s, mu, np.identity(3), np.zeros(3))
+    assert rel_fro(r2, R) < 1e-12 and rel_fro(t2, t) < 1e-12 and q < 1e-20
+
+
+def test_cpp_flavour_is_textbook_em():
+    """the C++ fitter's update (gmm_kernels.cu:135-210) equals standard full-covariance EM"""
+    rng = np.random.default_rng(0)
+    X = np.concatenate([rng.normal(0, 0.1, (300, 3)), rng.normal(1, 0.2, (200, 3))])
+    mu0 = X[[0, 400]]
+    w, mu, cov, ll = flat_gmm.cpp_fit(X, mu0, 3, sigma0_sq=0.05)
+    # one explicit textbook iteration chain
+    pi = np.array([0.5, 0.5]); m = mu0.copy(); S = np.tile(np.eye(3) * 0.05, (2, 1, 1))
+    for _ in range(3):
+        d = X[:, None, :] - m[None]
+        lg = -0.5 * (3 * np.log(2 * np.pi) + np.log(np.linalg.det(S))[None] + np.einsum("nja,jab,njb->nj", d, np.linalg.inv(S), d))
+        r = pi[None] * np.exp(lg); r /= r.sum(1, keepdims=True)
+        nk = r.sum(0); pi = nk / len(X); m = (r.T @ X) / nk[:, None]
+        d = X[:, None, :] - m[None]
+        S = np.einsum("nj,nja,njb->jab", r, d, d) / nk[:, None, None]
+    assert rel_fro(w, pi) < 1e-12 and rel_fro(mu, m) < 1e-12 and rel_fro(cov, S) < 1e-12
+    assert all(b >= a - 1e-9 for a, b in zip(ll, ll[1:]))       # EM never decreases the likelihood
