@@ -101,6 +101,8 @@ struct hgmm_ctx {
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms[3] = {0, 0, 0};
+    bool profiling = false;
+    std::vector<cudaEvent_t> pev;   // event pairs for per-launch timing
 
     // points (this rank's shard), SoA
     int n = 0;
@@ -233,6 +235,7 @@ int hgmm_destroy(hgmm_ctx* ctx) {
     if (ctx->h_dbl) cudaFreeHost(ctx->h_dbl);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HGMM_OK;
@@ -330,9 +333,19 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     ctx->launches += 1;
     const int tile = flat_pick_tile(ctx->n, ctx->num_sms, cfg->tile_points);
     CK(cudaEventRecord(ctx->ev0, s));
+    const bool prof = ctx->profiling;
+    if (prof) {
+        while ((int)ctx->pev.size() < 2 * cfg->max_iter) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            ctx->pev.push_back(e);
+        }
+    }
     for (int it = 0; it < cfg->max_iter; ++it) {
+        if (prof) CK(cudaEventRecord(ctx->pev[2 * it], s));
         CK(launch_em_flat(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, ctx->acc.as<double>(),
                           ctx->ctrl.as<int>(), ctx->num_sms, tile, s));
+        if (prof) CK(cudaEventRecord(ctx->pev[2 * it + 1], s));
         int r = allreduce(ctx, ctx->acc.as<double>(), kAccHdr + (size_t)J * kMom);
         if (r != HGMM_OK) return r;
         launch_flat_finalize(m, ctx->acc.as<double>(), ctx->ctrl.as<int>(), ctx->hist.as<double>(), (double)ctx->n_total, s);
@@ -352,7 +365,17 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     if (out_iters) *out_iters = ctx->h_ctrl[1];
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->last_ms[0] = ms; ctx->last_ms[1] = ms; ctx->last_ms[2] = 0;
+    ctx->last_ms[0] = ms; ctx->last_ms[1] = 0; ctx->last_ms[2] = 0;
+    if (prof) {
+        double sum = 0.0;
+        for (int it = 0; it < cfg->max_iter; ++it) {
+            float k = 0.f;
+            cudaEventElapsedTime(&k, ctx->pev[2 * it], ctx->pev[2 * it + 1]);
+            sum += k;
+        }
+        ctx->last_ms[1] = sum;
+        ctx->last_ms[2] = cfg->max_iter;
+    }
     ctx->have_flat = true;
     return HGMM_OK;
 }
@@ -777,6 +800,12 @@ int hgmm_measure_fp32_peak(hgmm_ctx* ctx, double* out_tflops) {
         if (rep > 0 && tf > best) best = tf;
     }
     *out_tflops = best;
+    return HGMM_OK;
+}
+
+int hgmm_set_profiling(hgmm_ctx* ctx, int on) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    ctx->profiling = on != 0;
     return HGMM_OK;
 }
 

@@ -243,7 +243,7 @@ __device__ double det3(const double M[3][3]) {
 }
 
 // ctrl: [0] done, [1] iterations, [2] numeric failure flag.  qstate: [0] previous q, [1] last q, [2] has-previous flag
-__global__ void __launch_bounds__(256) reg_solve_kernel(TreeModel t, const double* __restrict__ racc, int solver,
+__global__ void __launch_bounds__(128) reg_solve_kernel(TreeModel t, const double* __restrict__ racc, int solver,
                                                         double* __restrict__ Rt, double* __restrict__ q_hist,
                                                         double* __restrict__ qstate, int* __restrict__ ctrl, float tol) {
     if (ctrl[0]) return;
@@ -399,7 +399,7 @@ cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, 
 
 cudaError_t launch_reg_solve(const TreeModel& t, const double* racc, int solver, double* Rt, double* q_hist, double* qstate,
                              int* ctrl, float tol, cudaStream_t s) {
-    const int nth = 256;
+    const int nth = 128;                                    // 28 x 128 doubles = 28 KB of dynamic shared memory
     const size_t smem = (size_t)kSys * nth * sizeof(double);
     reg_solve_kernel<<<1, nth, smem, s>>>(t, racc, solver, Rt, q_hist, qstate, ctrl, tol);
     return cudaGetLastError();

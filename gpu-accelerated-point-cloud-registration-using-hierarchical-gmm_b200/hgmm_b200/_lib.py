@@ -67,6 +67,7 @@ SIGNATURES = {
     "hgmm_comm_destroy": (C.c_int, [_VP]),
     "hgmm_measure_fp32_peak": (C.c_int, [_VP, _VP]),
     "hgmm_last_timing": (C.c_int, [_VP, _VP]),
+    "hgmm_set_profiling": (C.c_int, [_VP, C.c_int]),
 }
 
 

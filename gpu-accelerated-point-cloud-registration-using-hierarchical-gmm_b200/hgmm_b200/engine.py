@@ -54,6 +54,9 @@ class Engine:
         self._check(self._lib.hgmm_last_timing(self._ctx, L.ptr(out)), "hgmm_last_timing")
         return out
 
+    def set_profiling(self, on):
+        self._check(self._lib.hgmm_set_profiling(self._ctx, int(bool(on))), "hgmm_set_profiling")
+
     def measure_fp32_peak(self):
         out = np.zeros(1)
         self._check(self._lib.hgmm_measure_fp32_peak(self._ctx, L.ptr(out)), "hgmm_measure_fp32_peak")

@@ -164,9 +164,13 @@ int hgmm_comm_destroy(hgmm_ctx* ctx);
 /* FP32 FMA throughput of this device in TFLOP/s (register-resident FFMA loop; the non-tensor
  * roofline denominator bench.py reports next to the HBM one) */
 int hgmm_measure_fp32_peak(hgmm_ctx* ctx, double* out_tflops);
-/* wall/device time of the kernels of the last fit/registration call, in ms (CUDA events on the
- * context stream): [0] total, [1] E/M kernels, [2] everything else */
+/* device time of the last fit/registration call in ms (CUDA events on the context stream):
+ * [0] whole enqueue-to-finish loop, [1] sum over the E/M sweep kernel launches alone (only when
+ * profiling is on, else 0), [2] number of E/M sweep launches that were timed */
 int hgmm_last_timing(const hgmm_ctx* ctx, double* out_ms3);
+/* on != 0: bracket every E/M sweep launch of the following fits with its own event pair (adds a few
+ * microseconds per launch; used by bench.py for the per-kernel roofline, never inside a timed step) */
+int hgmm_set_profiling(hgmm_ctx* ctx, int on);
 
 #ifdef __cplusplus
 }

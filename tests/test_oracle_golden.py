@@ -92,3 +92,13 @@ def test_cpp_flavour_is_textbook_em():
         S = np.einsum("nj,nja,njb->jab", r, d, d) / nk[:, None, None]
     assert rel_fro(w, pi) < 1e-12 and rel_fro(mu, m) < 1e-12 and rel_fro(cov, S) < 1e-12
     assert all(b >= a - 1e-9 for a, b in zip(ll, ll[1:]))       # EM never decreases the likelihood
+
+
+def test_c_oracle_agrees_with_numpy_oracle(bun000):
+    from oracle import c_oracle
+    X = bun000[::10]
+    rng = np.random.default_rng(1)
+    mu0 = X[rng.choice(len(X), 64, replace=False)]
+    w, mu, cov, ll = c_oracle.flat_fit(X, mu0, 5, 1e-4)
+    ow, omu, ocov, oll = flat_gmm.cpp_fit(X, mu0, 5, sigma0_sq=1e-4)
+    assert rel_fro(w, ow) < 1e-10 and rel_fro(mu, omu) < 1e-10 and rel_fro(cov, ocov) < 1e-9 and rel_fro(ll, oll) < 1e-12
