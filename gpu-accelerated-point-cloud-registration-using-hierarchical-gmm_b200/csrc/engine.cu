@@ -120,7 +120,7 @@ struct hgmm_ctx {
     // flat model
     FlatModel fm{};
     bool have_flat = false;
-    DevBuf f_means, f_covs, f_weights, f_invcov, f_packed, labels;
+    DevBuf f_means, f_covs, f_weights, f_invcov, f_packed, labels, done_at, partial, rowaux;
 
     // tree model + work
     TreeModel tm{};
@@ -221,7 +221,7 @@ int hgmm_destroy(hgmm_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf* all[] = {&ctx->bx, &ctx->by, &ctx->bz, &ctx->stage, &ctx->acc, &ctx->ctrl, &ctx->qstate, &ctx->hist, &ctx->f_means,
-                     &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
+                     &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->done_at, &ctx->partial, &ctx->rowaux, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
                      &ctx->t_cplx, &ctx->t_packed, &ctx->t_init, &ctx->p_group, &ctx->p_tilecnt, &ctx->p_tileoff, &ctx->p_segbase,
                      &ctx->p_seg0, &ctx->p_seg1, &ctx->p_chunkcnt, &ctx->p_chunkoff, &ctx->nchunks, &ctx->current, &ctx->tx, &ctx->ty,
                      &ctx->tz, &ctx->racc, &ctx->Rt};
@@ -329,9 +329,21 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     CK(cudaMemcpyAsync(m.weights, init_weights, (size_t)J * sizeof(float), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(ctx->acc.p, 0, acc_n * sizeof(double), s));
     CK(cudaMemsetAsync(ctx->ctrl.p, 0, 8 * sizeof(int), s));
+    CK(ctx->done_at.ensure((size_t)(cfg->max_iter + 2) * sizeof(int)));
+    CK(cudaMemsetAsync(ctx->done_at.p, 0, (size_t)(cfg->max_iter + 2) * sizeof(int), s));
+    int* done_at = ctx->done_at.as<int>();
     launch_flat_pack(m, 1, s);
     ctx->launches += 1;
+    // kernel variant: reserved == 1 selects the first-generation two-phase kernel (fp64 atomics), else the
+    // register-resident single-evaluation kernel with deterministic partial rows
+    const bool v1 = cfg->reserved == 1;
     const int tile = flat_pick_tile(ctx->n, ctx->num_sms, cfg->tile_points);
+    int JT = 1, W = 8, Sdiv = 1, G = 1, grid = 1, PB = 8;
+    if (!v1) {
+        flat2_plan(ctx->n, Jp, ctx->num_sms, cfg->tile_points, &JT, &W, &Sdiv, &G, &PB, &grid);
+        CK(ctx->partial.ensure((size_t)grid * G * kMom * Jp * sizeof(float)));
+        CK(ctx->rowaux.ensure((size_t)grid * G * 2 * sizeof(double)));
+    }
     CK(cudaEventRecord(ctx->ev0, s));
     const bool prof = ctx->profiling;
     if (prof) {
@@ -342,14 +354,26 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
         }
     }
     for (int it = 0; it < cfg->max_iter; ++it) {
+        if (v1) CK(cudaMemsetAsync(ctx->acc.p, 0, acc_n * sizeof(double), s));
         if (prof) CK(cudaEventRecord(ctx->pev[2 * it], s));
-        CK(launch_em_flat(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, ctx->acc.as<double>(),
-                          ctx->ctrl.as<int>(), ctx->num_sms, tile, s));
-        if (prof) CK(cudaEventRecord(ctx->pev[2 * it + 1], s));
+        if (v1) {
+            CK(launch_em_flat(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, ctx->acc.as<double>(),
+                              done_at + it, ctx->num_sms, tile, s));
+            ctx->launches += 1;
+        } else {
+            CK(launch_em_flat2(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, JT, W, Sdiv, G, grid,
+                               PB, ctx->partial.as<float>(), ctx->rowaux.as<double>(), done_at + it, s));
+            if (prof) CK(cudaEventRecord(ctx->pev[2 * it + 1], s));
+            CK(launch_flat_reduce(ctx->partial.as<float>(), ctx->rowaux.as<double>(), grid * G, m, ctx->acc.as<double>(),
+                                  done_at + it, s));
+            ctx->launches += 2;
+        }
+        if (prof && v1) CK(cudaEventRecord(ctx->pev[2 * it + 1], s));
         int r = allreduce(ctx, ctx->acc.as<double>(), kAccHdr + (size_t)J * kMom);
         if (r != HGMM_OK) return r;
-        launch_flat_finalize(m, ctx->acc.as<double>(), ctx->ctrl.as<int>(), ctx->hist.as<double>(), (double)ctx->n_total, s);
-        ctx->launches += 2;
+        launch_flat_finalize(m, ctx->acc.as<double>(), ctx->ctrl.as<int>(), done_at, it, ctx->hist.as<double>(),
+                             (double)ctx->n_total, s);
+        ctx->launches += 1;
     }
     CK(cudaEventRecord(ctx->ev1, s));
     CK(cudaGetLastError());

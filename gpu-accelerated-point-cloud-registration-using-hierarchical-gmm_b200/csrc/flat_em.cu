@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) em_flat_kernel(const float* __restrict__ 
     constexpr int TPH = TP / 2;
     constexpr int KS = 256 / TPH;          // J-splits in phase A
     static_assert(TPH >= 32 && KS >= 1, "tile too small/large");
-    if (ctrl[0]) return;                   // converged earlier: the rest of the enqueued iterations are no-ops
+    if (*ctrl) return;                     // converged earlier: the rest of the enqueued iterations are no-ops
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PackedComp* sp = reinterpret_cast<PackedComp*>(smem_raw);
@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) em_flat_kernel(const float* __restrict__ 
     float2* sms = reinterpret_cast<float2*>(spts + TP);
     __shared__ uint64_t bar;
     __shared__ double s_ll[8];
+    __shared__ double s_nl[8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) em_flat_kernel(const float* __restrict__ 
 
     const int pp = tid % TPH, ks = tid / TPH;
     const int Jq = Jp / KS;
-    double ll = 0.0;
+    double ll = 0.0, nlive = 0.0;
     const int nTiles = (n + TP - 1) / TP;
     for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
         const int base = tile * TP;
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(256) em_flat_kernel(const float* __restrict__ 
             const bool valid = (base + p) < n;
             const bool finite = norm2 > kNegBig;
             if (valid) ll += (double)(norm2 * kLn2);
+            if (valid && finite && lse2 > kNegBig) nlive += 1.0;
             reinterpret_cast<float*>(spts + p)[3] = (valid && finite) ? norm2 : INFINITY;   // +inf => gamma = 0
         }
         __syncthreads();
@@ -257,40 +259,53 @@ __global__ void __launch_bounds__(256) em_flat_kernel(const float* __restrict__ 
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
-    if (lane == 0) s_ll[warp] = ll;
+    for (int o = 16; o > 0; o >>= 1) {
+        ll += __shfl_xor_sync(0xffffffffu, ll, o);
+        nlive += __shfl_xor_sync(0xffffffffu, nlive, o);
+    }
+    if (lane == 0) {
+        s_ll[warp] = ll;
+        s_nl[warp] = nlive;
+    }
     __syncthreads();
     if (tid == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += s_ll[w];
+        double t = 0.0, c = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            t += s_ll[w];
+            c += s_nl[w];
+        }
         atomicAdd(acc, t);
+        atomicAdd(acc + 1, c);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// finalize: moments -> parameters (fp64), stopping rule, re-pack.  One CTA of 1024 threads.
+// finalize: moments -> parameters (fp64), stopping rule, re-pack.  128 components per CTA.
+// done_at[it] is written only by iteration it-1 (block 0), so every kernel of iteration `it` reads a
+// settled flag; acc[0] = sum log-lik, acc[1] = number of live points (= sum_j N_j), set before this runs.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) flat_finalize_kernel(FlatModel m, double* __restrict__ acc, int* __restrict__ ctrl,
-                                                             double* __restrict__ ll_hist, double n_total) {
-    if (ctrl[0]) return;
-    __shared__ double red[32];
-    __shared__ double s_total;
-    const int tid = threadIdx.x;
-    double part = 0.0;
-    for (int j = tid; j < m.J; j += blockDim.x) part += acc[kAccHdr + (size_t)j * kMom];
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((tid & 31) == 0) red[tid >> 5] = part;
-    __syncthreads();
-    if (tid == 0) {
-        double t = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-        s_total = t;
+__global__ void __launch_bounds__(128) flat_finalize_kernel(FlatModel m, const double* __restrict__ acc, int* __restrict__ ctrl,
+                                                            int* __restrict__ done_at, int it, double* __restrict__ ll_hist,
+                                                            double n_total) {
+    const bool done = done_at[it] != 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (done) {
+            done_at[it + 1] = 1;
+        } else {
+            const double ll = (m.flavor == HGMM_FLAVOR_PY) ? acc[0] / n_total : acc[0];
+            ll_hist[it] = ll;
+            const bool conv = (m.flavor == HGMM_FLAVOR_PY) && it > 0 && fabs(ll - ll_hist[it - 1]) < (double)m.tol;
+            done_at[it + 1] = conv ? 1 : 0;
+            ctrl[1] = it + 1;
+            ctrl[0] = conv ? 1 : 0;
+        }
     }
-    __syncthreads();
-    const double total = s_total;
-
-    for (int j = tid; j < m.J; j += blockDim.x) {
-        double* A = acc + kAccHdr + (size_t)j * kMom;
+    if (done) return;
+    const double total = acc[1];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m.J) return;
+    {
+        const double* A = acc + kAccHdr + (size_t)j * kMom;
         const double M0 = A[0];
         const double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
         PackedComp p;
@@ -319,7 +334,6 @@ __global__ void __launch_bounds__(1024) flat_finalize_kernel(FlatModel m, double
             const double w = nk / n_total;
             m.weights[j] = (float)w;
             m.means[3 * j] = (float)mean[0]; m.means[3 * j + 1] = (float)mean[1]; m.means[3 * j + 2] = (float)mean[2];
-            // pack from the float-rounded values the caller will see
             p = pack_diag(log((double)(float)w + 1e-8), (float)mean[0], (float)mean[1], (float)mean[2], iv[0], iv[1], iv[2], 3);
         } else {
             // gmm_kernels.cu:156-210: pi = N_j / sum N_k; mu = weighted mean; Sigma centred on the NEW mu
@@ -343,16 +357,6 @@ __global__ void __launch_bounds__(1024) flat_finalize_kernel(FlatModel m, double
             }
         }
         m.packed[j] = p;
-#pragma unroll
-        for (int k = 0; k < kMom; ++k) A[k] = 0.0;
-    }
-    if (tid == 0) {
-        const int it = ctrl[1];
-        const double ll = (m.flavor == HGMM_FLAVOR_PY) ? acc[0] / n_total : acc[0];
-        ll_hist[it] = ll;
-        if (m.flavor == HGMM_FLAVOR_PY && it > 0 && fabs(ll - ll_hist[it - 1]) < (double)m.tol) ctrl[0] = 1;
-        ctrl[1] = it + 1;
-        acc[0] = 0.0;
     }
 }
 
@@ -483,8 +487,9 @@ void launch_aos_to_soa_transform(const float* xyz, int64_t n, const double* Rt, 
 void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s) {
     flat_pack_kernel<<<(m.Jp + 127) / 128, 128, 0, s>>>(m, first);
 }
-void launch_flat_finalize(const FlatModel& m, double* acc, int* ctrl, double* ll_hist, double n_total, cudaStream_t s) {
-    flat_finalize_kernel<<<1, 1024, 0, s>>>(m, acc, ctrl, ll_hist, n_total);
+void launch_flat_finalize(const FlatModel& m, const double* acc, int* ctrl, int* done_at, int it, double* ll_hist, double n_total,
+                          cudaStream_t s) {
+    flat_finalize_kernel<<<(m.J + 127) / 128, 128, 0, s>>>(m, acc, ctrl, done_at, it, ll_hist, n_total);
 }
 
 template <int TP, int JT>

@@ -46,7 +46,14 @@ struct TreeWork {
 void launch_aos_to_soa(const float* xyz, int64_t n, float* x, float* y, float* z, cudaStream_t s);
 void launch_aos_to_soa_transform(const float* xyz, int64_t n, const double* Rt, float* x, float* y, float* z, cudaStream_t s);
 void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s);
-void launch_flat_finalize(const FlatModel& m, double* acc, int* ctrl, double* ll_hist, double n_total, cudaStream_t s);
+void launch_flat_finalize(const FlatModel& m, const double* acc, int* ctrl, int* done_at, int it, double* ll_hist, double n_total,
+                          cudaStream_t s);
+// flat_em2.cu
+void flat2_plan(int n, int Jp, int num_sms, int pb_request, int* JT, int* W, int* Sdiv, int* G, int* PB, int* grid);
+cudaError_t launch_em_flat2(const float* x, const float* y, const float* z, int n, const FlatModel& m, int JT, int W, int Sdiv,
+                            int G, int grid, int PB, float* partial, double* rowaux, const int* done_flag, cudaStream_t s);
+cudaError_t launch_flat_reduce(const float* partial, const double* rowaux, int rows, const FlatModel& m, double* acc,
+                               const int* done_flag, cudaStream_t s);
 int flat_pick_tile(int n, int num_sms, int requested);
 cudaError_t launch_em_flat(const float* x, const float* y, const float* z, int n, const FlatModel& m, double* acc,
                            const int* ctrl, int num_sms, int tile_points, cudaStream_t s);

@@ -90,7 +90,7 @@ class Engine:
 
     # -- flat mixture ------------------------------------------------------------------------
     def fit_flat(self, means, covs, weights, cov_type="full", flavor=None, max_iter=10, tol=0.0, sigma_bug=False,
-                 tile_points=0, want_outputs=True):
+                 tile_points=0, want_outputs=True, variant=0):
         ct = L.COV_TYPES[cov_type]
         if flavor is None:
             flavor = L.FLAVOR_CPP if ct == L.COV_FULL else L.FLAVOR_PY
@@ -99,7 +99,7 @@ class Engine:
         ce = {L.COV_FULL: (J, 3, 3), L.COV_DIAG: (J, 3), L.COV_SPHERICAL: (J,)}[ct]
         covs = L.f32c(covs, ce)
         weights = L.f32c(weights, (J,))
-        cfg = L.FlatConfig(J, ct, flavor, int(max_iter), float(tol), int(bool(sigma_bug)), int(tile_points), 0)
+        cfg = L.FlatConfig(J, ct, flavor, int(max_iter), float(tol), int(bool(sigma_bug)), int(tile_points), int(variant))
         o_means = np.empty((J, 3), np.float32) if want_outputs else None
         o_covs = np.empty(ce, np.float32) if want_outputs else None
         o_w = np.empty(J, np.float32) if want_outputs else None

@@ -1,0 +1,23 @@
+"""GPU probe (not a bench line): device time of one 10-iteration fit of configs[1] for every kernel variant."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gpu-accelerated-point-cloud-registration-using-hierarchical-gmm_b200"))
+import numpy as np, torch, hgmm_b200
+X = np.load(os.path.join(ROOT, "tests/golden/bun000_xyz.npy"))
+out = {}
+eng = hgmm_b200.Engine(0)
+eng.set_points(torch.from_numpy(X).cuda())
+for J in (800, 100, 1024, 256):
+    rng = np.random.default_rng(1)
+    mu0 = X[rng.choice(len(X), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J, 1, 1)); w0 = np.full(J, 1 / J, np.float32)
+    for name, variant, tile in (("v2_pb8", 0, 8), ("v2_pb4", 0, 4), ("v1_t64", 1, 64), ("v1_t128", 1, 128)):
+        eng.set_profiling(False)
+        for _ in range(3):
+            eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False, variant=variant, tile_points=tile)
+        tot = [float(eng.last_timing_ms()[0]) for _ in range(5) if eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False, variant=variant, tile_points=tile)]
+        eng.set_profiling(True)
+        eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False, variant=variant, tile_points=tile)
+        k = eng.last_timing_ms()
+        out["J%d_%s" % (J, name)] = {"fit10_ms_min": min(tot), "sweep_kernel_us": 1e3 * k[1] / max(k[2], 1)}
+print(json.dumps(out, indent=1))

@@ -83,14 +83,13 @@ def test_flat_full_config2_matches_c_oracle(engine, bun000, J, sig):
     r = engine.fit_flat(mu0, cov0, np.full(J, 1.0 / J, np.float32), cov_type="full", max_iter=10)
     ow, omu, ocov, oll = c_oracle.flat_fit(X, mu0, 10, np.float32(sig))
     assert np.isfinite(ocov).all()
-    assert rel_fro(r["weights"], ow) < TOL
-    assert rel_fro(r["means"], omu) < TOL
-    assert rel_fro(r["covs"], ocov) < (5 * TOL if sig == 1.0 else TOL)
-    assert rel_fro(r["ll"], oll) < TOL
+    errs = (rel_fro(r["weights"], ow), rel_fro(r["means"], omu), rel_fro(r["covs"], ocov), rel_fro(r["ll"], oll))
+    print("J=%d sig=%g rel_fro (w, mu, cov, ll) = %.2e %.2e %.2e %.2e" % ((J, sig) + errs))
+    assert max(errs) < TOL, errs
 
 
-@pytest.mark.parametrize("tile", [64, 128, 256, 512])
-def test_flat_full_tile_sizes_agree(engine, bun000, tile):
+@pytest.mark.parametrize("variant,tile", [(0, 4), (0, 8), (1, 64), (1, 128), (1, 256), (1, 512)])
+def test_flat_kernel_variants_agree(engine, bun000, variant, tile):
     from oracle import flat_gmm
     X = bun000[::5]
     rng = np.random.default_rng(2)
@@ -98,9 +97,38 @@ def test_flat_full_tile_sizes_agree(engine, bun000, tile):
     mu0 = X[rng.choice(len(X), J, replace=False)]
     cov0 = np.tile(np.eye(3, dtype=np.float32) * 2e-4, (J, 1, 1))
     engine.set_points(X)
-    r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=4, tile_points=tile)
+    r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=4, tile_points=tile, variant=variant)
     ow, omu, ocov, _ = flat_gmm.cpp_fit(X, mu0, 4, sigma0_sq=np.float32(2e-4))
     assert rel_fro(r["means"], omu) < TOL and rel_fro(r["covs"], ocov) < TOL and rel_fro(r["weights"], ow) < TOL
+
+
+@pytest.mark.parametrize("J", [1, 5, 31, 32, 33, 64, 100, 129, 160, 161, 512, 544, 545])
+def test_flat_component_count_sweep(engine, bun000, J):
+    """every slot/group configuration of the sweep kernel (ragged J, 1..16 warps per group)"""
+    from oracle import flat_gmm
+    X = bun000[::3]
+    rng = np.random.default_rng(J)
+    mu0 = X[rng.choice(len(X), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * 3e-4, (J, 1, 1))
+    engine.set_points(X)
+    r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=3)
+    ow, omu, ocov, oll = flat_gmm.cpp_fit(X, mu0, 3, sigma0_sq=np.float32(3e-4))
+    assert rel_fro(r["means"], omu) < TOL and rel_fro(r["covs"], ocov) < TOL and rel_fro(r["weights"], ow) < TOL
+    assert rel_fro(r["ll"], oll) < TOL
+
+
+def test_flat_run_to_run_deterministic(engine, bun000):
+    """partial rows + fixed-order fp64 reduction: two runs are bit-identical"""
+    X = bun000
+    J = 800
+    rng = np.random.default_rng(1)
+    mu0 = X[rng.choice(len(X), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J, 1, 1))
+    engine.set_points(X)
+    a = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=10)
+    b = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=10)
+    assert (a["means"] == b["means"]).all() and (a["covs"] == b["covs"]).all() and (a["weights"] == b["weights"]).all()
+    assert (a["ll"] == b["ll"]).all()
 
 
 def test_flat_full_sigma_bug_flag(engine, bun000):
@@ -189,13 +217,18 @@ def test_tree_lidar_properties(engine):
     L = 4
     init = X[hgmm_tree.reference_init_indices(L)]
     engine.set_points(X)
-    r = engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4.0, ll_mode="estep")
+    r = engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=25.0, ll_mode="estep")
     nt = hgmm_tree.n_total(L)
     assert r["pi"].shape == (nt,)
+    prev = 1.0 + 1e-5
     for l in range(L):
         lb, le = hgmm_tree.level(l), hgmm_tree.level(l + 1)
         s = float(r["pi"][lb:le].astype(np.float64).sum())
-        assert 0.98 < s <= 1.0 + 1e-5, (l, s)                 # mass only leaks through dead points/blank nodes
+        # the reference semantics drop a point whose 8 child densities all fall below 1e-15 (hgmm_gpu.py:404-406),
+        # so level mass can only shrink with depth and never exceed 1
+        assert s <= prev + 1e-5 and s > 0.5, (l, s)
+        prev = s
+    assert float(r["pi"][:8].astype(np.float64).sum()) > 0.99
     cur = r["current"]
     lb = hgmm_tree.level(L - 1)
     assert cur.min() >= lb and cur.max() < nt
@@ -293,7 +326,7 @@ def test_bunny_registration_recovers_ground_truth(engine, bun000, bun045):
     engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep")
     engine.reg_set_target(bun045)
     # start from a coarse guess (25 deg about y): GMM-tree registration is local
-    th = np.deg2rad(-25.0)
+    th = np.deg2rad(25.0)
     R0 = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
     rot, t, qq, it, _ = engine.register_tree(rot=R0, t=np.zeros(3), solver="twist_lstsq", maxiter=60, tol=1e-6, lambda_c=0.01)
     ang = np.rad2deg(np.arccos(np.clip((np.trace(rot @ Rq) - 1) / 2, -1, 1)))      # rot ~ Rq^T
