@@ -120,7 +120,7 @@ struct hgmm_ctx {
     // flat model
     FlatModel fm{};
     bool have_flat = false;
-    DevBuf f_means, f_covs, f_weights, f_invcov, f_packed, labels, done_at, partial, rowaux;
+    DevBuf f_means, f_covs, f_weights, f_invcov, f_packed, labels, done_at, partial, rowaux, cref;
 
     // tree model + work
     TreeModel tm{};
@@ -221,7 +221,7 @@ int hgmm_destroy(hgmm_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf* all[] = {&ctx->bx, &ctx->by, &ctx->bz, &ctx->stage, &ctx->acc, &ctx->ctrl, &ctx->qstate, &ctx->hist, &ctx->f_means,
-                     &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->done_at, &ctx->partial, &ctx->rowaux, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
+                     &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->done_at, &ctx->partial, &ctx->rowaux, &ctx->cref, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
                      &ctx->t_cplx, &ctx->t_packed, &ctx->t_init, &ctx->p_group, &ctx->p_tilecnt, &ctx->p_tileoff, &ctx->p_segbase,
                      &ctx->p_seg0, &ctx->p_seg1, &ctx->p_chunkcnt, &ctx->p_chunkoff, &ctx->nchunks, &ctx->current, &ctx->tx, &ctx->ty,
                      &ctx->tz, &ctx->racc, &ctx->Rt};
@@ -323,6 +323,8 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     m.J = J; m.Jp = Jp; m.cov_type = cfg->cov_type; m.flavor = cfg->flavor; m.sigma_bug = cfg->sigma_bug; m.tol = cfg->tol;
     m.means = ctx->f_means.as<float>(); m.covs = ctx->f_covs.as<float>(); m.weights = ctx->f_weights.as<float>();
     m.inv_cov = ctx->f_invcov.as<float>(); m.packed = ctx->f_packed.as<PackedComp>();
+    CK(ctx->cref.ensure((size_t)(Jp / 128 + 2) * sizeof(float)));
+    m.cref_blocks = ctx->cref.as<float>();
     cudaStream_t s = ctx->stream;
     CK(cudaMemcpyAsync(m.means, init_means, (size_t)J * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(m.covs, init_covs, (size_t)J * ce * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -338,9 +340,9 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     // register-resident single-evaluation kernel with deterministic partial rows
     const bool v1 = cfg->reserved == 1;
     const int tile = flat_pick_tile(ctx->n, ctx->num_sms, cfg->tile_points);
-    int JT = 1, W = 8, Sdiv = 1, G = 1, grid = 1, PB = 8;
+    int JT = 1, W = 8, Sdiv = 1, G = 1, grid = 1, big = 0;
     if (!v1) {
-        flat2_plan(ctx->n, Jp, ctx->num_sms, cfg->tile_points, &JT, &W, &Sdiv, &G, &PB, &grid);
+        flat2_plan(ctx->n, Jp, ctx->num_sms, cfg->tile_points == 1, &JT, &W, &Sdiv, &G, &grid, &big);
         CK(ctx->partial.ensure((size_t)grid * G * kMom * Jp * sizeof(float)));
         CK(ctx->rowaux.ensure((size_t)grid * G * 2 * sizeof(double)));
     }
@@ -361,8 +363,8 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
                               done_at + it, ctx->num_sms, tile, s));
             ctx->launches += 1;
         } else {
-            CK(launch_em_flat2(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, JT, W, Sdiv, G, grid,
-                               PB, ctx->partial.as<float>(), ctx->rowaux.as<double>(), done_at + it, s));
+            CK(launch_em_flat2(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, m.cref_blocks, JT, W, Sdiv,
+                               G, grid, big, ctx->partial.as<float>(), ctx->rowaux.as<double>(), done_at + it, s));
             if (prof) CK(cudaEventRecord(ctx->pev[2 * it + 1], s));
             CK(launch_flat_reduce(ctx->partial.as<float>(), ctx->rowaux.as<double>(), grid * G, m, ctx->acc.as<double>(),
                                   done_at + it, s));

@@ -65,13 +65,24 @@ __device__ __forceinline__ PackedComp pack_diag(double logw, double mx, double m
 
 // One thread per (padded) component: model arrays -> PackedComp.  first=1 reproduces
 // gmm_impl.py:122 (inv_cov = 1/sqrt(cov) before the loop), otherwise :134.
-__global__ void flat_pack_kernel(FlatModel m, int first) {
+// max of c2 over the (128-thread) block -> cref_blocks[blockIdx.x]; every thread of the block must call it
+__device__ __forceinline__ void block_max_c2(float c2, float* __restrict__ cref_blocks) {
+    __shared__ float s_c2[4];
+    float v = c2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) s_c2[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) cref_blocks[blockIdx.x] = fmaxf(fmaxf(s_c2[0], s_c2[1]), fmaxf(s_c2[2], s_c2[3]));
+}
+
+__global__ void __launch_bounds__(128) flat_pack_kernel(FlatModel m, int first) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m.Jp) return;
     PackedComp p;
     if (j >= m.J) {
         p = pack_full(-INFINITY, 0, 0, 0, Sym3{1, 0, 0, 1, 0, 1}, false, 0.0);
-        m.packed[j] = p;
+        if (j < m.Jp) m.packed[j] = p;
+        block_max_c2(-INFINITY, m.cref_blocks);
         return;
     }
     double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
@@ -91,6 +102,7 @@ __global__ void flat_pack_kernel(FlatModel m, int first) {
         p = pack_full(log(w), mx, my, mz, s, m.sigma_bug != 0, 0.0);
     }
     m.packed[j] = p;
+    block_max_c2(p.c2, m.cref_blocks);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -303,8 +315,8 @@ __global__ void __launch_bounds__(128) flat_finalize_kernel(FlatModel m, const d
     if (done) return;
     const double total = acc[1];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m.J) return;
-    {
+    float my_c2 = -INFINITY;
+    if (j < m.J) {
         const double* A = acc + kAccHdr + (size_t)j * kMom;
         const double M0 = A[0];
         const double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
@@ -357,7 +369,9 @@ __global__ void __launch_bounds__(128) flat_finalize_kernel(FlatModel m, const d
             }
         }
         m.packed[j] = p;
+        my_c2 = p.c2;
     }
+    block_max_c2(my_c2, m.cref_blocks);
 }
 
 // ------------------------------------------------------------------------------------------

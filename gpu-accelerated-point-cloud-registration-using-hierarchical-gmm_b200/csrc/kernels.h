@@ -19,6 +19,7 @@ struct FlatModel {
     float* weights;            // [Jp]
     float* inv_cov;            // PY flavour: 1/std, [Jp,3] | [Jp]
     PackedComp* packed;        // [Jp]
+    float* cref_blocks;        // [ceil(Jp/128)] max c2 of each block of 128 components (reference for the sweep)
 };
 
 struct TreeModel {
@@ -49,9 +50,10 @@ void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s);
 void launch_flat_finalize(const FlatModel& m, const double* acc, int* ctrl, int* done_at, int it, double* ll_hist, double n_total,
                           cudaStream_t s);
 // flat_em2.cu
-void flat2_plan(int n, int Jp, int num_sms, int pb_request, int* JT, int* W, int* Sdiv, int* G, int* PB, int* grid);
-cudaError_t launch_em_flat2(const float* x, const float* y, const float* z, int n, const FlatModel& m, int JT, int W, int Sdiv,
-                            int G, int grid, int PB, float* partial, double* rowaux, const int* done_flag, cudaStream_t s);
+void flat2_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* JT, int* W, int* Sdiv, int* G, int* grid, int* big);
+cudaError_t launch_em_flat2(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
+                            int JT, int W, int Sdiv, int G, int grid, int big, float* partial, double* rowaux,
+                            const int* done_flag, cudaStream_t s);
 cudaError_t launch_flat_reduce(const float* partial, const double* rowaux, int rows, const FlatModel& m, double* acc,
                                const int* done_flag, cudaStream_t s);
 int flat_pick_tile(int n, int num_sms, int requested);
