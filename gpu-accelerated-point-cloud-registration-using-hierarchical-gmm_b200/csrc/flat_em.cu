@@ -77,32 +77,28 @@ __device__ __forceinline__ void block_max_c2(float c2, float* __restrict__ cref_
 }
 
 __global__ void __launch_bounds__(128) flat_pack_kernel(FlatModel m, int first) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    PackedComp p;
-    if (j >= m.J) {
-        p = pack_full(-INFINITY, 0, 0, 0, Sym3{1, 0, 0, 1, 0, 1}, false, 0.0);
-        if (j < m.Jp) m.packed[j] = p;
-        block_max_c2(-INFINITY, m.cref_blocks);
-        return;
-    }
-    double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
-    double w = m.weights[j];
-    if (m.flavor == HGMM_FLAVOR_PY) {
-        double iv[3];
-        for (int d = 0; d < 3; ++d) {
-            double c = (m.cov_type == HGMM_COV_SPHERICAL) ? (double)m.covs[j] : (double)m.covs[3 * j + d];
-            iv[d] = first ? 1.0 / sqrt(c) : 1.0 / (sqrt(c + 1e-6) + 1e-8);
-            if (m.cov_type == HGMM_COV_SPHERICAL) { if (d == 0) m.inv_cov[j] = (float)iv[0]; }
-            else m.inv_cov[3 * j + d] = (float)iv[d];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    PackedComp p = pack_full(-INFINITY, 0, 0, 0, Sym3{1, 0, 0, 1, 0, 1}, false, 0.0);     // padding: dead component
+    if (j < m.J) {
+        const double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
+        const double w = m.weights[j];
+        if (m.flavor == HGMM_FLAVOR_PY) {
+            double iv[3];
+            for (int d = 0; d < 3; ++d) {
+                const double c = (m.cov_type == HGMM_COV_SPHERICAL) ? (double)m.covs[j] : (double)m.covs[3 * j + d];
+                iv[d] = first ? 1.0 / sqrt(c) : 1.0 / (sqrt(c + 1e-6) + 1e-8);
+                if (m.cov_type == HGMM_COV_SPHERICAL) { if (d == 0) m.inv_cov[j] = (float)iv[0]; }
+                else m.inv_cov[3 * j + d] = (float)iv[d];
+            }
+            p = pack_diag(log(w + 1e-8), mx, my, mz, iv[0], iv[1], iv[2], 3);
+        } else {
+            const float* c = m.covs + 9 * j;
+            Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
+            p = pack_full(log(w), mx, my, mz, s, m.sigma_bug != 0, 0.0);
         }
-        p = pack_diag(log(w + 1e-8), mx, my, mz, iv[0], iv[1], iv[2], 3);
-    } else {
-        const float* c = m.covs + 9 * j;
-        Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
-        p = pack_full(log(w), mx, my, mz, s, m.sigma_bug != 0, 0.0);
     }
-    m.packed[j] = p;
-    block_max_c2(p.c2, m.cref_blocks);
+    if (j < m.Jp) m.packed[j] = p;
+    block_max_c2(p.c2, m.cref_blocks);       // single convergent call site: full-mask shuffles + __syncthreads inside
 }
 
 // ------------------------------------------------------------------------------------------
