@@ -339,10 +339,15 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     // kernel variant: reserved == 1 selects the first-generation two-phase kernel (fp64 atomics), else the
     // register-resident single-evaluation kernel with deterministic partial rows
     const bool v1 = cfg->reserved == 1;
+    const bool v3 = !v1 && cfg->reserved != 2 && Jp >= 64;      // packed-FP32 kernel needs at least one component pair per lane
     const int tile = flat_pick_tile(ctx->n, ctx->num_sms, cfg->tile_points);
     int JT = 1, W = 8, Sdiv = 1, G = 1, grid = 1, big = 0;
-    if (!v1) {
+    if (v3) {
+        flat3_plan(ctx->n, Jp, ctx->num_sms, cfg->tile_points == 1, &W, &Sdiv, &G, &grid, &big);
+    } else if (!v1) {
         flat2_plan(ctx->n, Jp, ctx->num_sms, cfg->tile_points == 1, &JT, &W, &Sdiv, &G, &grid, &big);
+    }
+    if (!v1) {
         CK(ctx->partial.ensure((size_t)grid * G * kMom * Jp * sizeof(float)));
         CK(ctx->rowaux.ensure((size_t)grid * G * 2 * sizeof(double)));
     }
@@ -363,8 +368,12 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
                               done_at + it, ctx->num_sms, tile, s));
             ctx->launches += 1;
         } else {
-            CK(launch_em_flat2(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, m.cref_blocks, JT, W, Sdiv,
-                               G, grid, big, ctx->partial.as<float>(), ctx->rowaux.as<double>(), done_at + it, s));
+            if (v3)
+                CK(launch_em_flat3(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, m.cref_blocks, W, Sdiv, G,
+                                   grid, big, ctx->partial.as<float>(), ctx->rowaux.as<double>(), done_at + it, s));
+            else
+                CK(launch_em_flat2(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, m.cref_blocks, JT, W, Sdiv,
+                                   G, grid, big, ctx->partial.as<float>(), ctx->rowaux.as<double>(), done_at + it, s));
             if (prof) CK(cudaEventRecord(ctx->pev[2 * it + 1], s));
             CK(launch_flat_reduce(ctx->partial.as<float>(), ctx->rowaux.as<double>(), grid * G, m, ctx->acc.as<double>(),
                                   done_at + it, s));
@@ -812,20 +821,23 @@ int hgmm_measure_fp32_peak(hgmm_ctx* ctx, double* out_tflops) {
     CK(cudaSetDevice(ctx->device));
     CK(ctx->hist.ensure(64));
     const int blocks = ctx->num_sms * 8, iters = 4096;
-    double best = 0.0;
-    for (int rep = 0; rep < 4; ++rep) {
-        CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        CK(launch_ffma_peak(ctx->hist.as<float>(), blocks, iters, ctx->stream));
-        CK(cudaEventRecord(ctx->ev1, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->launches += 1;
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-        const double flops = (double)blocks * 256.0 * iters * 16.0 * 8.0 * 2.0;
-        const double tf = flops / (ms * 1e-3) / 1e12;
-        if (rep > 0 && tf > best) best = tf;
+    for (int mode = 0; mode < 3; ++mode) {
+        double best = 0.0;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaEventRecord(ctx->ev0, ctx->stream));
+            if (mode < 2) CK(launch_ffma_peak(ctx->hist.as<float>(), blocks, iters, mode, ctx->stream));
+            else CK(launch_ffma2_peak(ctx->hist.as<float>(), blocks, iters, ctx->stream));
+            CK(cudaEventRecord(ctx->ev1, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->launches += 1;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            const double flops = (double)blocks * 256.0 * iters * 16.0 * 8.0 * 2.0 * (mode == 2 ? 2.0 : 1.0);
+            const double tf = flops / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best) best = tf;
+        }
+        out_tflops[mode] = best;
     }
-    *out_tflops = best;
     return HGMM_OK;
 }
 

@@ -465,17 +465,24 @@ __global__ void __launch_bounds__(256) scan_components_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------
-// FP32 peak probe: 8 independent FFMA chains per thread
+// FP32 peak probes: 8 independent FFMA chains per thread.
+//   mode 0: multiplier/addend are compile-time constants (FFMA immediate form)
+//   mode 1: multiplier/addend live in registers (the 3-register FFMA every real kernel issues)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float seed) {
+template <int MODE>
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float seed, float bv, float cv) {
     float a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
-    const float b = 1.0000001f, c = 1e-7f;
+    float b = 1.0000001f, c = 1e-7f;
+    float b2 = b, c2 = c;
+    if (MODE == 1) {
+        b = bv; c = cv; b2 = bv * 1.0000002f; c2 = cv * 0.5f;      // runtime values: no immediate encoding possible
+    }
 #pragma unroll 1
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
-            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b2, c2); a2 = fmaf(a2, b, c2); a3 = fmaf(a3, b2, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b2, c2); a6 = fmaf(a6, b, c2); a7 = fmaf(a7, b2, c);
         }
     }
     float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
@@ -576,8 +583,9 @@ cudaError_t launch_level_ll(const float* x, const float* y, const float* z, int 
     return cudaGetLastError();
 }
 
-cudaError_t launch_ffma_peak(float* out, int blocks, int iters, cudaStream_t s) {
-    ffma_peak_kernel<<<blocks, 256, 0, s>>>(out, iters, 0.5f);
+cudaError_t launch_ffma_peak(float* out, int blocks, int iters, int mode, cudaStream_t s) {
+    if (mode == 0) ffma_peak_kernel<0><<<blocks, 256, 0, s>>>(out, iters, 0.5f, 1.0000001f, 1e-7f);
+    else ffma_peak_kernel<1><<<blocks, 256, 0, s>>>(out, iters, 0.5f, 1.0000001f, 1e-7f);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,385 @@
+// flat_em3.cu -- packed-FP32 (FFMA2) fused E+M sweep of the flat mixture: the default path for J > 32.
+//
+// Same contract and data flow as flat_em2.cu's single-evaluation kernel (expectationStep +
+// maximizationStep of src/c++/gmm_fit/gmm_kernels.cu:278-350; e_step + m_step of
+// src/python/gmm_waymo/src/gmm_impl.py:90-116), re-expressed for Blackwell's packed FP32 pipe:
+// a 3-register FFMA issues at half rate on sm_100, the two-wide FFMA2/FADD2/FMUL2 (PTX *.f32x2)
+// restore the full 128 FMA/clk/SM.  Every lane therefore owns a PAIR of components (slots sw and
+// sw + Sdiv) whose parameters, e = 2^(q - Cref) values and 10 centred moment accumulators are
+// float2 registers; point coordinates are staged in shared memory already duplicated (x,x,y,y,z,z)
+// so a broadcast LDS.128 pair feeds both halves.
+//
+// Per batch of 8 points: pass 1 (q, e, per-point partial sums) -> register reduce-scatter ->
+// partial sums to shared memory -> ONE group barrier -> every warp redundantly finishes the 8
+// sums (no second barrier, partial buffers double-buffered by batch parity) -> pass 2 (moments).
+// Batches containing a point whose sum underflows the fixed reference take an exact max-shifted
+// path.  Partial moment rows + fixed-order fp64 reduction are shared with flat_em2.cu.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hgmm {
+
+constexpr int kChunk3 = 512;            // points staged in shared memory at a time (32 B each, duplicated)
+constexpr int kPB3 = 8;                 // points per batch
+constexpr float kUnder3 = 7.888609052210118e-31f;   // 2^-100
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 f2u(float2 v) { return *reinterpret_cast<u64*>(&v); }
+__device__ __forceinline__ float2 u2f(u64 v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2u(a)), "l"(f2u(b)), "l"(f2u(c)));
+    return u2f(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2u(a)), "l"(f2u(b)));
+    return u2f(d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2u(a)), "l"(f2u(b)));
+    return u2f(d);
+}
+
+__device__ __forceinline__ void group_bar3(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// reduce v[0..8) over the warp; lane L ends with point idx(L) = 4*bit4 + 2*bit3 + bit2 in v[0]
+__device__ __forceinline__ void reduce_scatter8(float* v, int lane, bool is_max) {
+    const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = u4 ? v[i + 4] : v[i], send = u4 ? v[i] : v[i + 4];
+        const float o = __shfl_xor_sync(0xffffffffu, send, 16);
+        v[i] = is_max ? fmaxf(keep, o) : keep + o;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = u3 ? v[i + 2] : v[i], send = u3 ? v[i] : v[i + 2];
+        const float o = __shfl_xor_sync(0xffffffffu, send, 8);
+        v[i] = is_max ? fmaxf(keep, o) : keep + o;
+    }
+    {
+        const float keep = u2 ? v[1] : v[0], send = u2 ? v[0] : v[1];
+        const float o = __shfl_xor_sync(0xffffffffu, send, 4);
+        v[0] = is_max ? fmaxf(keep, o) : keep + o;
+    }
+#pragma unroll
+    for (int off = 2; off > 0; off >>= 1) {
+        const float o = __shfl_xor_sync(0xffffffffu, v[0], off);
+        v[0] = is_max ? fmaxf(v[0], o) : v[0] + o;
+    }
+}
+
+struct PairParams {            // two components side by side; means stored negated so d = P + nm is one FADD2
+    float2 nmx, nmy, nmz, c2;
+    float2 axx, ayy, azz, axy, axz, ayz;
+};
+
+__device__ __forceinline__ float2 quad2(const PairParams& k, float2 X, float2 Y, float2 Z, float2& dx, float2& dy, float2& dz) {
+    dx = fadd2(X, k.nmx);
+    dy = fadd2(Y, k.nmy);
+    dz = fadd2(Z, k.nmz);
+    float2 t0 = fmul2(k.axz, dz);
+    t0 = ffma2(k.axy, dy, t0);
+    t0 = ffma2(k.axx, dx, t0);
+    float2 t1 = fmul2(k.ayz, dz);
+    t1 = ffma2(k.ayy, dy, t1);
+    const float2 t2 = fmul2(k.azz, dz);
+    float2 q = ffma2(dz, t2, k.c2);
+    q = ffma2(dy, t1, q);
+    q = ffma2(dx, t0, q);
+    return q;
+}
+
+// grid.x CTAs; blockDim.x = 32 * G * Sdiv; G independent groups of Sdiv warps; warp sw of a group owns the
+// component slots sw (low half of every pair) and sw + Sdiv (high half); lane = component inside the slot.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                              const float* __restrict__ pz, int n,
+                                                              const PackedComp* __restrict__ packed,
+                                                              const float* __restrict__ cref_blocks, int n_cref, int J, int Jp,
+                                                              int Sdiv, int G, float* __restrict__ partial,
+                                                              double* __restrict__ rowaux, const int* __restrict__ done_flag,
+                                                              float norm_eps_on) {
+    if (*done_flag) return;
+    constexpr int PB = kPB3;
+    __shared__ __align__(16) float4 spts[kChunk3][2];            // (x,x,y,y) (z,z,0,0)
+    __shared__ __align__(16) float red[2][8][PB][16];            // [batch parity][group][point][warp of group]
+    __shared__ __align__(16) float2 fin[16][PB];                 // [warp][point] (inv, inv) -- private to each warp
+    __shared__ __align__(16) float finmax[8][PB];                // [group][point] exact maximum (rare path)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = warp / Sdiv, sw = warp - g * Sdiv;
+    const int gthreads = Sdiv * 32;
+    const int S = Jp >> 5;
+    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+
+    float cref = -INFINITY;
+    for (int i = 0; i < n_cref; ++i) cref = fmaxf(cref, __ldg(cref_blocks + i));
+    if (!(cref > kNegBig)) cref = 0.f;
+
+    // ---- the lane's component pair -> registers
+    PairParams k;
+    bool live0, live1;
+    {
+        const int s0 = sw, s1 = sw + Sdiv;
+        live0 = s0 < S;
+        live1 = s1 < S;
+        const float4* a4 = reinterpret_cast<const float4*>(packed + (live0 ? s0 * 32 + lane : 0));
+        const float4* b4 = reinterpret_cast<const float4*>(packed + (live1 ? s1 * 32 + lane : 0));
+        const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), a2 = __ldg(a4 + 2);
+        const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1), b2 = __ldg(b4 + 2);
+        k.nmx = make_float2(-a0.x, -b0.x);
+        k.nmy = make_float2(-a0.y, -b0.y);
+        k.nmz = make_float2(-a0.z, -b0.z);
+        k.c2 = make_float2(live0 ? a0.w - cref : -INFINITY, live1 ? b0.w - cref : -INFINITY);
+        k.axx = make_float2(a1.x, b1.x);
+        k.ayy = make_float2(a1.y, b1.y);
+        k.azz = make_float2(a1.z, b1.z);
+        k.axy = make_float2(a1.w, b1.w);
+        k.axz = make_float2(a2.x, b2.x);
+        k.ayz = make_float2(a2.y, b2.y);
+    }
+    float2 a[kMom];
+#pragma unroll
+    for (int m = 0; m < kMom; ++m) a[m] = make_float2(0.f, 0.f);
+    double ll = 0.0, nlive = 0.0;                         // accumulated by the finishing lanes of warp sw == 0
+
+    const int per = (int)(((long long)n + gridDim.x - 1) / gridDim.x);
+    const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
+    int parity = 0;
+
+    for (int cb = lo; cb < hi; cb += kChunk3) {
+        const int cn = min(kChunk3, hi - cb);
+        __syncthreads();
+        for (int i = tid; i < cn; i += blockDim.x) {
+            const float x = px[cb + i], y = py[cb + i], z = pz[cb + i];
+            spts[i][0] = make_float4(x, x, y, y);
+            spts[i][1] = make_float4(z, z, 0.f, 0.f);
+        }
+        __syncthreads();
+        const int gper = (cn + G - 1) / G;
+        const int gs = min(cn, g * gper), ge = min(cn, gs + gper);
+        for (int b = gs; b < ge; b += PB) {
+            const int np = min(PB, ge - b);
+            float2 e[PB];
+            float sm[PB];
+            // ---------------- pass 1
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                const int ip = min(b + p, cn - 1);
+                const float4 P0 = spts[ip][0], P1 = spts[ip][1];
+                float2 dx, dy, dz;
+                const float2 q = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
+                e[p] = make_float2(ex2f(q.x), ex2f(q.y));
+                sm[p] = e[p].x + e[p].y;
+            }
+            reduce_scatter8(sm, lane, false);
+            if ((lane & 3) == 0) red[parity][g][ridx][sw] = sm[0];
+            group_bar3(1 + g, gthreads);
+            // ---------------- every warp finishes the 8 sums itself (lanes 0..7), no second barrier
+            bool under = false;
+            {
+                float v = 0.f;
+                if (lane < PB) {
+                    for (int w = 0; w < Sdiv; ++w) v += red[parity][g][lane][w];
+                }
+                const bool valid = lane < np;
+                under = valid && !(v >= kUnder3);
+                float inv = 0.f;
+                if (valid && !under) {
+                    const float lse2 = cref + lg2f(v);
+                    float norm2 = lse2, scale = 1.0f;
+                    if (norm_eps_on != 0.f) {              // gmm_impl.py:113  log(sum exp + 1e-8)
+                        const float Mx = fmaxf(lse2, kLog2Eps8);
+                        norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
+                        scale = ex2f(lse2 - norm2);
+                    }
+                    inv = scale / v;
+                    if (sw == 0) {
+                        ll += (double)(norm2 * kLn2);
+                        nlive += 1.0;
+                    }
+                }
+                if (lane < PB) fin[warp][lane] = make_float2(inv, inv);
+            }
+            const unsigned any_under = __ballot_sync(0xffffffffu, under);
+            if (any_under) {
+                // ---------------- rare path: exact per-point maximum
+                float mx[PB];
+#pragma unroll
+                for (int p = 0; p < PB; ++p) {
+                    const int ip = min(b + p, cn - 1);
+                    const float4 P0 = spts[ip][0], P1 = spts[ip][1];
+                    float2 dx, dy, dz;
+                    const float2 q = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
+                    e[p] = q;
+                    mx[p] = fmaxf(fmaxf(q.x, q.y), kNegBig);
+                }
+                reduce_scatter8(mx, lane, true);
+                group_bar3(1 + g, gthreads);               // everyone is done reading red[parity] (first use)
+                if ((lane & 3) == 0) red[parity][g][ridx][sw] = mx[0];
+                group_bar3(1 + g, gthreads);
+                if (sw == 0 && lane < PB) {
+                    float v = kNegBig;
+                    for (int w = 0; w < Sdiv; ++w) v = fmaxf(v, red[parity][g][lane][w]);
+                    finmax[g][lane] = v;
+                }
+                group_bar3(1 + g, gthreads);
+#pragma unroll
+                for (int p = 0; p < PB; ++p) {
+                    const float m = finmax[g][p];
+                    e[p] = make_float2(ex2f(e[p].x - m), ex2f(e[p].y - m));
+                    sm[p] = e[p].x + e[p].y;
+                }
+                reduce_scatter8(sm, lane, false);
+                if ((lane & 3) == 0) red[parity][g][ridx][sw] = sm[0];     // maxima were consumed before the last barrier
+                group_bar3(1 + g, gthreads);
+                {
+                    float v = 0.f;
+                    if (lane < PB) {
+                        for (int w = 0; w < Sdiv; ++w) v += red[parity][g][lane][w];
+                    }
+                    const float m = lane < PB ? finmax[g][lane] : 0.f;
+                    const bool valid = lane < np;
+                    float inv = 0.f;
+                    if (valid && v > 0.f && m > kNegBig) {
+                        const float lse2 = cref + m + lg2f(v);
+                        float norm2 = lse2, scale = 1.0f;
+                        if (norm_eps_on != 0.f) {
+                            const float Mx = fmaxf(lse2, kLog2Eps8);
+                            norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
+                            scale = ex2f(lse2 - norm2);
+                        }
+                        inv = scale / v;
+                        if (sw == 0 && under) {            // the fast path left only the underflowed points out
+                            ll += (double)(norm2 * kLn2);
+                            nlive += 1.0;
+                        }
+                    } else if (valid && under && sw == 0 && norm_eps_on != 0.f) {
+                        ll += (double)(kLog2Eps8 * kLn2);   // log(0 + 1e-8)
+                    }
+                    if (lane < PB) fin[warp][lane] = make_float2(inv, inv);
+                }
+            }
+            __syncwarp();
+            // ---------------- pass 2: moments
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                const int ip = min(b + p, cn - 1);
+                const float4 P0 = spts[ip][0], P1 = spts[ip][1];
+                const float2 inv2 = fin[warp][p];
+                const float2 gam = fmul2(e[p], inv2);
+                const float2 dx = fadd2(make_float2(P0.x, P0.y), k.nmx);
+                const float2 dy = fadd2(make_float2(P0.z, P0.w), k.nmy);
+                const float2 dz = fadd2(make_float2(P1.x, P1.y), k.nmz);
+                const float2 gx = fmul2(gam, dx), gy = fmul2(gam, dy), gz = fmul2(gam, dz);
+                a[0] = fadd2(a[0], gam);
+                a[1] = fadd2(a[1], gx);
+                a[2] = fadd2(a[2], gy);
+                a[3] = fadd2(a[3], gz);
+                a[4] = ffma2(gx, dx, a[4]);
+                a[5] = ffma2(gx, dy, a[5]);
+                a[6] = ffma2(gx, dz, a[6]);
+                a[7] = ffma2(gy, dy, a[7]);
+                a[8] = ffma2(gy, dz, a[8]);
+                a[9] = ffma2(gz, dz, a[9]);
+            }
+            __syncwarp();                                  // fin[warp] is rewritten by the next batch's finishing lanes
+            parity ^= 1;
+        }
+    }
+    // ---- partial rows: partial[row][m][Jp], row = blockIdx * G + g
+    const size_t row = (size_t)blockIdx.x * G + g;
+    float* dst = partial + row * (size_t)kMom * Jp;
+    if (live0) {
+        const int j = sw * 32 + lane;
+#pragma unroll
+        for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].x;
+    }
+    if (live1) {
+        const int j = (sw + Sdiv) * 32 + lane;
+#pragma unroll
+        for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].y;
+    }
+    if (sw == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ll += __shfl_xor_sync(0xffffffffu, ll, o);
+            nlive += __shfl_xor_sync(0xffffffffu, nlive, o);
+        }
+        if (lane == 0) {
+            rowaux[2 * row] = ll;
+            rowaux[2 * row + 1] = nlive;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// packed-FP32 peak probe (mode 2 of hgmm_measure_fp32_peak): 8 independent FFMA2 chains, register operands
+__global__ void __launch_bounds__(256) ffma2_peak_kernel(float* out, int iters, float seed, float bv, float cv) {
+    float2 a0 = make_float2(seed, seed + 1), a1 = make_float2(seed + 2, seed + 3), a2 = make_float2(seed + 4, seed + 5),
+           a3 = make_float2(seed + 6, seed + 7), a4 = make_float2(seed + 8, seed + 9), a5 = make_float2(seed + 10, seed + 11),
+           a6 = make_float2(seed + 12, seed + 13), a7 = make_float2(seed + 14, seed + 15);
+    const float2 b = make_float2(bv, bv * 1.0000002f), c = make_float2(cv, cv * 0.5f);
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = ffma2(a0, b, c); a1 = ffma2(a1, b, c); a2 = ffma2(a2, b, c); a3 = ffma2(a3, b, c);
+            a4 = ffma2(a4, b, c); a5 = ffma2(a5, b, c); a6 = ffma2(a6, b, c); a7 = ffma2(a7, b, c);
+        }
+    }
+    const float2 r = fadd2(fadd2(fadd2(a0, a1), fadd2(a2, a3)), fadd2(fadd2(a4, a5), fadd2(a6, a7)));
+    if (r.x + r.y == 12345.678f) out[0] = r.x;
+}
+
+cudaError_t launch_ffma2_peak(float* out, int blocks, int iters, cudaStream_t s) {
+    ffma2_peak_kernel<<<blocks, 256, 0, s>>>(out, iters, 0.5f, 1.0000001f, 1e-7f);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename K>
+static int occ_blocks(K kern, int threads) {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0) != cudaSuccess || occ < 1) occ = 1;
+    return occ;
+}
+
+// (Sdiv, G, W, grid, big) for the packed kernel; requires S = Jp/32 >= 2
+void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdiv, int* G, int* grid, int* big) {
+    const int S = Jp / 32;
+    const int sdiv = (S + 1) / 2;                   // warps per group: each warp owns slots sw and sw + sdiv
+    int g = 1;
+    if (sdiv <= 4) g = 8 / sdiv;                    // small mixtures: several independent groups per CTA
+    const int w = sdiv * g;
+    *big = (w > 13 || one_cta_per_sm) ? 1 : 0;
+    int occ = *big ? occ_blocks(em_flat3_kernel<512, 1>, w * 32) : occ_blocks(em_flat3_kernel<416, 2>, w * 32);
+    if (occ > 4) occ = 4;
+    if (w >= 8 && occ > 2) occ = 2;
+    int ctas = occ * num_sms;
+    const long long min_pts = 2LL * kPB3 * g;
+    if ((long long)ctas * min_pts > n) ctas = (int)((n + min_pts - 1) / min_pts);
+    if (ctas < 1) ctas = 1;
+    *W = w; *Sdiv = sdiv; *G = g; *grid = ctas;
+}
+
+cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
+                            int W, int Sdiv, int G, int grid, int big, float* partial, double* rowaux, const int* done_flag,
+                            cudaStream_t s) {
+    const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
+    const int ncref = (m.Jp + 127) / 128;
+    if (big)
+        em_flat3_kernel<512, 1><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
+                                                       done_flag, eps_on);
+    else
+        em_flat3_kernel<416, 2><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
+                                                       done_flag, eps_on);
+    return cudaGetLastError();
+}
+
+}  // namespace hgmm

@@ -63,7 +63,14 @@ cudaError_t launch_predict(const float* x, const float* y, const float* z, int n
                            int32_t* labels, int num_sms, cudaStream_t s);
 cudaError_t launch_level_ll(const float* x, const float* y, const float* z, int n, const PackedComp* packed, int Jp,
                             double* acc, int num_sms, cudaStream_t s);
-cudaError_t launch_ffma_peak(float* out, int blocks, int iters, cudaStream_t s);
+cudaError_t launch_ffma_peak(float* out, int blocks, int iters, int mode, cudaStream_t s);
+
+// flat_em3.cu (packed FP32)
+void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdiv, int* G, int* grid, int* big);
+cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
+                            int W, int Sdiv, int G, int grid, int big, float* partial, double* rowaux, const int* done_flag,
+                            cudaStream_t s);
+cudaError_t launch_ffma2_peak(float* out, int blocks, int iters, cudaStream_t s);
 
 // tree_em.cu
 void launch_tree_init(const TreeModel& t, const float* init_means, float sig2, cudaStream_t s);

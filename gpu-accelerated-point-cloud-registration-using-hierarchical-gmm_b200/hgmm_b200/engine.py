@@ -58,9 +58,10 @@ class Engine:
         self._check(self._lib.hgmm_set_profiling(self._ctx, int(bool(on))), "hgmm_set_profiling")
 
     def measure_fp32_peak(self):
-        out = np.zeros(1)
+        """-> TFLOP/s of (immediate-operand FFMA, 3-register FFMA, packed FFMA2)"""
+        out = np.zeros(3)
         self._check(self._lib.hgmm_measure_fp32_peak(self._ctx, L.ptr(out)), "hgmm_measure_fp32_peak")
-        return float(out[0])
+        return float(out[0]), float(out[1]), float(out[2])
 
     @staticmethod
     def _cloud_arg(points):

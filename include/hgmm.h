@@ -72,7 +72,7 @@ typedef struct hgmm_flat_config {
     float tol;                     /* PY flavour: stop when |d mean-log-lik| < tol; CPP flavour ignores it */
     int32_t sigma_bug;             /* CPP flavour only: reproduce gmm_kernels.cu:97-103 (d^T Sigma d) */
     int32_t tile_points;           /* 0 = auto; points per CTA tile (64,128,256,512) */
-    int32_t reserved;              /* kernel variant: 0 = default (single-evaluation kernel), 1 = first-generation two-phase kernel */
+    int32_t reserved;              /* kernel variant: 0 = default (packed-FP32 sweep), 1 = first-generation two-phase kernel, 2 = scalar single-evaluation kernel */
 } hgmm_flat_config;
 
 typedef struct hgmm_tree_config {
@@ -161,8 +161,10 @@ int hgmm_comm_init(hgmm_ctx* ctx, int rank, int nranks, const void* id128);
 int hgmm_comm_destroy(hgmm_ctx* ctx);
 
 /* ---- measurement helper ---- */
-/* FP32 FMA throughput of this device in TFLOP/s (register-resident FFMA loop; the non-tensor
- * roofline denominator bench.py reports next to the HBM one) */
+/* FP32 FMA throughput of this device in TFLOP/s, out_tflops[3]: [0] scalar FFMA with immediate
+ * operands, [1] scalar FFMA with three register operands, [2] packed FFMA2 (fma.rn.f32x2) with
+ * register operands -- the pipe the sweep kernels run on and the non-tensor roofline denominator
+ * bench.py reports next to the HBM one */
 int hgmm_measure_fp32_peak(hgmm_ctx* ctx, double* out_tflops);
 /* device time of the last fit/registration call in ms (CUDA events on the context stream):
  * [0] whole enqueue-to-finish loop, [1] sum over the E/M sweep kernel launches alone (only when
