@@ -357,7 +357,10 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
     int g = 1;
     if (sdiv <= 4) g = 8 / sdiv;                    // small mixtures: several independent groups per CTA
     const int w = sdiv * g;
-    *big = (w > 13 || one_cta_per_sm) ? 1 : 0;
+    // >= 8 warps per CTA: one register-rich CTA per SM (126 registers, no spills) measured faster on B200 than two
+    // 72-register CTAs (71.5 vs 77.6 us on configs[1]); smaller CTAs co-reside 2-4 per SM.  one_cta_per_sm == 1 forces
+    // the register-rich build, == 2 the two-CTA build (profiling switches).
+    *big = (one_cta_per_sm == 1 || (one_cta_per_sm == 0 && w >= 8) || w > 13) ? 1 : 0;
     int occ = *big ? occ_blocks(em_flat3_kernel<512, 1>, w * 32) : occ_blocks(em_flat3_kernel<416, 2>, w * 32);
     if (occ > 4) occ = 4;
     if (w >= 8 && occ > 2) occ = 2;
