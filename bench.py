@@ -167,10 +167,10 @@ def main():
         hdist.attach_communicator(eng)
 
     X, src = load_cloud()
+    mu0, cov0, w0 = init_model(X)      # the replicated model starts identical on every rank
     if world > 1:       # weak scaling: a same-size shard per rank (the cloud jittered by a rank-seeded 10 um)
         X = (X + np.random.default_rng(100 + rank).normal(0, 1e-5, X.shape)).astype(np.float32)
     n = len(X)
-    mu0, cov0, w0 = init_model(X)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # 256 MiB > 126 MB L2
 
     def barrier():

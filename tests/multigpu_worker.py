@@ -1,0 +1,79 @@
+"""torchrun worker for tests/test_multigpu.py: sharded fits (NCCL all-reduce inside libhgmm) must equal the
+single-GPU fit of the whole cloud."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "gpu-accelerated-point-cloud-registration-using-hierarchical-gmm_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def rel_fro(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import hgmm_b200
+    from hgmm_b200 import dist as hd, hgmm as H
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    X = np.load(os.path.join(ROOT, "tests", "golden", "bun000_xyz.npy"))[::2]
+    shard = hd.shuffled_shard(X, rank, world, seed=5)
+    eng = hgmm_b200.Engine(local)
+    hd.attach_communicator(eng)
+    eng.set_points(shard)
+    assert eng.total_points == len(X), (eng.total_points, len(X))
+    ok = True
+    # ---- flat, both flavours
+    J = 96
+    mu0 = X[np.random.default_rng(2).choice(len(X), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * 2e-4, (J, 1, 1))
+    w0 = np.full(J, 1 / J, np.float32)
+    r = eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=6)
+    rd = eng.fit_flat(mu0, np.full((J, 3), 2e-4, np.float32), w0, cov_type="diag", max_iter=6)
+    # ---- tree
+    L = 3
+    init = X[H.reference_init_indices(L)]
+    tr = eng.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="level", want_current=False)
+    tre = eng.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False)
+    # ---- registration with a sharded target
+    th = np.deg2rad(6.0)
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    T = (X @ R.T + np.array([0.002, -0.001, 0.003])).astype(np.float32)
+    eng.reg_set_target(hd.shuffled_shard(T, rank, world, seed=6))
+    rot, t, q, it, _ = eng.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+    if rank == 0:
+        ref = hgmm_b200.Engine(local)          # no communicator: the whole cloud on one GPU
+        ref.set_points(X)
+        s = ref.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=6)
+        sd = ref.fit_flat(mu0, np.full((J, 3), 2e-4, np.float32), w0, cov_type="diag", max_iter=6)
+        ts = ref.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="level", want_current=False)
+        tse = ref.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False)
+        ref.reg_set_target(T)
+        rot1, t1, q1, it1, _ = ref.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+        errs = {
+            "flat_full": max(rel_fro(r["means"], s["means"]), rel_fro(r["covs"], s["covs"]), rel_fro(r["weights"], s["weights"]), rel_fro(r["ll"], s["ll"])),
+            "flat_diag": max(rel_fro(rd["means"], sd["means"]), rel_fro(rd["covs"], sd["covs"]), rel_fro(rd["weights"], sd["weights"])),
+            "tree_level": max(rel_fro(tr["pi"], ts["pi"]), rel_fro(tr["mu"], ts["mu"]), rel_fro(tr["cov"], ts["cov"])),
+            "tree_estep": max(rel_fro(tre["pi"], tse["pi"]), rel_fro(tre["mu"], tse["mu"]), rel_fro(tre["cov"], tse["cov"])),
+            "reg": max(rel_fro(rot, rot1), float(np.abs(t - t1).max())),
+        }
+        print("MULTIGPU", world, errs, "iters", tr["iters"].tolist(), ts["iters"].tolist(), it, it1, flush=True)
+        ok = all(v < 2e-5 for v in errs.values()) and tr["iters"].tolist() == ts["iters"].tolist() and it == it1
+        ref.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    eng.comm_destroy()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
