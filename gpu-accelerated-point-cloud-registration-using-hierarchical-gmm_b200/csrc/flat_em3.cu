@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
     __shared__ __align__(16) float finmax[8][PB];                // [group][point] exact maximum (rare path)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 2 * 8 * PB * 16; i += blockDim.x) (&red[0][0][0][0])[i] = 0.f;     // slots >= Sdiv stay zero
     const int g = warp / Sdiv, sw = warp - g * Sdiv;
     const int gthreads = Sdiv * 32;
     const int S = Jp >> 5;
@@ -180,31 +181,33 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
             reduce_scatter8(sm, lane, false);
             if ((lane & 3) == 0) red[parity][g][ridx][sw] = sm[0];
             group_bar3(1 + g, gthreads);
-            // ---------------- every warp finishes the 8 sums itself (lanes 0..7), no second barrier
+            // ---------------- every warp finishes the 8 sums itself (lanes 0..7), no second barrier.
+            // red[..][point][0..16) is contiguous and zero beyond Sdiv: 4 LDS.128 + 15 FADD, no loop.
             bool under = false;
-            {
-                float v = 0.f;
-                if (lane < PB) {
-                    for (int w = 0; w < Sdiv; ++w) v += red[parity][g][lane][w];
-                }
+            if (lane < PB) {
+                const float4* r4 = reinterpret_cast<const float4*>(&red[parity][g][lane][0]);
+                const float4 r0 = r4[0], r1 = r4[1], r2 = r4[2], r3 = r4[3];
+                const float v = (((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w))) +
+                                (((r2.x + r2.y) + (r2.z + r2.w)) + ((r3.x + r3.y) + (r3.z + r3.w)));
                 const bool valid = lane < np;
                 under = valid && !(v >= kUnder3);
-                float inv = 0.f;
-                if (valid && !under) {
-                    const float lse2 = cref + lg2f(v);
-                    float norm2 = lse2, scale = 1.0f;
-                    if (norm_eps_on != 0.f) {              // gmm_impl.py:113  log(sum exp + 1e-8)
-                        const float Mx = fmaxf(lse2, kLog2Eps8);
-                        norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
-                        scale = ex2f(lse2 - norm2);
-                    }
-                    inv = scale / v;
-                    if (sw == 0) {
-                        ll += (double)(norm2 * kLn2);
-                        nlive += 1.0;
+                float inv = (valid && !under) ? __fdividef(1.0f, v) : 0.f;
+                if (norm_eps_on != 0.f || sw == 0) {       // only the PY flavour rescales; only warp 0 of the group keeps the log-lik
+                    if (valid && !under) {
+                        const float lse2 = cref + lg2f(v);
+                        float norm2 = lse2;
+                        if (norm_eps_on != 0.f) {          // gmm_impl.py:113  log(sum exp + 1e-8)
+                            const float Mx = fmaxf(lse2, kLog2Eps8);
+                            norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
+                            inv *= ex2f(lse2 - norm2);
+                        }
+                        if (sw == 0) {
+                            ll += (double)(norm2 * kLn2);
+                            nlive += 1.0;
+                        }
                     }
                 }
-                if (lane < PB) fin[warp][lane] = make_float2(inv, inv);
+                fin[warp][lane] = make_float2(inv, inv);
             }
             const unsigned any_under = __ballot_sync(0xffffffffu, under);
             if (any_under) {
