@@ -46,8 +46,34 @@ __device__ __forceinline__ void group_bar3(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// reduce v[0..8) over the warp; lane L ends with point idx(L) = 4*bit4 + 2*bit3 + bit2 in v[0]
-__device__ __forceinline__ void reduce_scatter8(float* v, int lane, bool is_max) {
+// reduce v[0..PB) over the warp (PB = 8 or 4); lane L ends with point idx(L) in v[0]:
+//   PB = 8: idx = 4*bit4 + 2*bit3 + bit2;  PB = 4: idx = 2*bit4 + bit3
+template <int PB>
+__device__ __forceinline__ void reduce_scatter(float* v, int lane, bool is_max);
+
+template <>
+__device__ __forceinline__ void reduce_scatter<4>(float* v, int lane, bool is_max) {
+    const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = u4 ? v[i + 2] : v[i], send = u4 ? v[i] : v[i + 2];
+        const float o = __shfl_xor_sync(0xffffffffu, send, 16);
+        v[i] = is_max ? fmaxf(keep, o) : keep + o;
+    }
+    {
+        const float keep = u3 ? v[1] : v[0], send = u3 ? v[0] : v[1];
+        const float o = __shfl_xor_sync(0xffffffffu, send, 8);
+        v[0] = is_max ? fmaxf(keep, o) : keep + o;
+    }
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+        const float o = __shfl_xor_sync(0xffffffffu, v[0], off);
+        v[0] = is_max ? fmaxf(v[0], o) : v[0] + o;
+    }
+}
+
+template <>
+__device__ __forceinline__ void reduce_scatter<8>(float* v, int lane, bool is_max) {
     const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -96,7 +122,7 @@ __device__ __forceinline__ float2 quad2(const PairParams& k, float2 X, float2 Y,
 
 // grid.x CTAs; blockDim.x = 32 * G * Sdiv; G independent groups of Sdiv warps; warp sw of a group owns the
 // component slots sw (low half of every pair) and sw + Sdiv (high half); lane = component inside the slot.
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, int PB>
 __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __restrict__ px, const float* __restrict__ py,
                                                               const float* __restrict__ pz, int n,
                                                               const PackedComp* __restrict__ packed,
@@ -105,7 +131,6 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
                                                               double* __restrict__ rowaux, const int* __restrict__ done_flag,
                                                               float norm_eps_on) {
     if (*done_flag) return;
-    constexpr int PB = kPB3;
     __shared__ __align__(16) float4 spts[kChunk3][2];            // (x,x,y,y) (z,z,0,0)
     __shared__ __align__(16) float red[2][8][PB][16];            // [batch parity][group][point][warp of group]
     __shared__ __align__(16) float2 fin[16][PB];                 // [warp][point] (inv, inv) -- private to each warp
@@ -116,7 +141,8 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
     const int g = warp / Sdiv, sw = warp - g * Sdiv;
     const int gthreads = Sdiv * 32;
     const int S = Jp >> 5;
-    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const int ridx = PB == 8 ? ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1) : ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    const bool rwriter = PB == 8 ? (lane & 3) == 0 : (lane & 7) == 0;
 
     float cref = -INFINITY;
     for (int i = 0; i < n_cref; ++i) cref = fmaxf(cref, __ldg(cref_blocks + i));
@@ -178,8 +204,8 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
                 e[p] = make_float2(ex2f(q.x), ex2f(q.y));
                 sm[p] = e[p].x + e[p].y;
             }
-            reduce_scatter8(sm, lane, false);
-            if ((lane & 3) == 0) red[parity][g][ridx][sw] = sm[0];
+            reduce_scatter<PB>(sm, lane, false);
+            if (rwriter) red[parity][g][ridx][sw] = sm[0];
             group_bar3(1 + g, gthreads);
             // ---------------- every warp finishes the 8 sums itself (lanes 0..7), no second barrier.
             // red[..][point][0..16) is contiguous and zero beyond Sdiv: 4 LDS.128 + 15 FADD, no loop.
@@ -222,9 +248,9 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
                     e[p] = q;
                     mx[p] = fmaxf(fmaxf(q.x, q.y), kNegBig);
                 }
-                reduce_scatter8(mx, lane, true);
+                reduce_scatter<PB>(mx, lane, true);
                 group_bar3(1 + g, gthreads);               // everyone is done reading red[parity] (first use)
-                if ((lane & 3) == 0) red[parity][g][ridx][sw] = mx[0];
+                if (rwriter) red[parity][g][ridx][sw] = mx[0];
                 group_bar3(1 + g, gthreads);
                 if (sw == 0 && lane < PB) {
                     float v = kNegBig;
@@ -238,8 +264,8 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
                     e[p] = make_float2(ex2f(e[p].x - m), ex2f(e[p].y - m));
                     sm[p] = e[p].x + e[p].y;
                 }
-                reduce_scatter8(sm, lane, false);
-                if ((lane & 3) == 0) red[parity][g][ridx][sw] = sm[0];     // maxima were consumed before the last barrier
+                reduce_scatter<PB>(sm, lane, false);
+                if (rwriter) red[parity][g][ridx][sw] = sm[0];     // maxima were consumed before the last barrier
                 group_bar3(1 + g, gthreads);
                 {
                     float v = 0.f;
@@ -364,7 +390,7 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
     // 72-register CTAs (71.5 vs 77.6 us on configs[1]); smaller CTAs co-reside 2-4 per SM.  one_cta_per_sm == 1 forces
     // the register-rich build, == 2 the two-CTA build (profiling switches).
     *big = (one_cta_per_sm == 1 || (one_cta_per_sm == 0 && w >= 8) || w > 13) ? 1 : 0;
-    int occ = *big ? occ_blocks(em_flat3_kernel<512, 1>, w * 32) : occ_blocks(em_flat3_kernel<416, 2>, w * 32);
+    int occ = *big ? occ_blocks(em_flat3_kernel<512, 1, 8>, w * 32) : occ_blocks(em_flat3_kernel<416, 2, 4>, w * 32);
     if (occ > 4) occ = 4;
     if (w >= 8 && occ > 2) occ = 2;
     int ctas = occ * num_sms;
@@ -380,10 +406,10 @@ cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int 
     const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
     const int ncref = (m.Jp + 127) / 128;
     if (big)
-        em_flat3_kernel<512, 1><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
+        em_flat3_kernel<512, 1, 8><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
                                                        done_flag, eps_on);
     else
-        em_flat3_kernel<416, 2><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
+        em_flat3_kernel<416, 2, 4><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
                                                        done_flag, eps_on);
     return cudaGetLastError();
 }

@@ -11,7 +11,7 @@ for J in (800, 100, 1024, 256):
     rng = np.random.default_rng(1)
     mu0 = X[rng.choice(len(X), J, replace=False)]
     cov0 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J, 1, 1)); w0 = np.full(J, 1 / J, np.float32)
-    for name, variant, tile in (("v3_2cta", 0, 0), ("v3_1cta", 0, 1), ("v2_scalar", 2, 1), ("v1_t64", 1, 64)):
+    for name, variant, tile in (("v3_big_pb8", 0, 1), ("v3_2cta_pb4", 0, 2), ("v2_scalar", 2, 1)):
         eng.set_profiling(False)
         for _ in range(3):
             eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False, variant=variant, tile_points=tile)
