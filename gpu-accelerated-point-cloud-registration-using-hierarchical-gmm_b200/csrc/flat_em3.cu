@@ -122,7 +122,7 @@ __device__ __forceinline__ float2 quad2(const PairParams& k, float2 X, float2 Y,
 
 // grid.x CTAs; blockDim.x = 32 * G * Sdiv; G independent groups of Sdiv warps; warp sw of a group owns the
 // component slots sw (low half of every pair) and sw + Sdiv (high half); lane = component inside the slot.
-template <int MAXT, int MINB, int PB>
+template <int MAXT, int MINB, int PB, int NP>
 __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __restrict__ px, const float* __restrict__ py,
                                                               const float* __restrict__ pz, int n,
                                                               const PackedComp* __restrict__ packed,
@@ -148,31 +148,34 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
     for (int i = 0; i < n_cref; ++i) cref = fmaxf(cref, __ldg(cref_blocks + i));
     if (!(cref > kNegBig)) cref = 0.f;
 
-    // ---- the lane's component pair -> registers
-    PairParams k;
-    bool live0, live1;
-    {
-        const int s0 = sw, s1 = sw + Sdiv;
-        live0 = s0 < S;
-        live1 = s1 < S;
-        const float4* a4 = reinterpret_cast<const float4*>(packed + (live0 ? s0 * 32 + lane : 0));
-        const float4* b4 = reinterpret_cast<const float4*>(packed + (live1 ? s1 * 32 + lane : 0));
+    // ---- the lane's NP component pairs -> registers; pair u = slots (sw + 2u*Sdiv, sw + (2u+1)*Sdiv)
+    PairParams k[NP];
+    bool live0[NP], live1[NP];
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+        const int s0 = sw + (2 * u) * Sdiv, s1 = sw + (2 * u + 1) * Sdiv;
+        live0[u] = s0 < S;
+        live1[u] = s1 < S;
+        const float4* a4 = reinterpret_cast<const float4*>(packed + (live0[u] ? s0 * 32 + lane : 0));
+        const float4* b4 = reinterpret_cast<const float4*>(packed + (live1[u] ? s1 * 32 + lane : 0));
         const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), a2 = __ldg(a4 + 2);
         const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1), b2 = __ldg(b4 + 2);
-        k.nmx = make_float2(-a0.x, -b0.x);
-        k.nmy = make_float2(-a0.y, -b0.y);
-        k.nmz = make_float2(-a0.z, -b0.z);
-        k.c2 = make_float2(live0 ? a0.w - cref : -INFINITY, live1 ? b0.w - cref : -INFINITY);
-        k.axx = make_float2(a1.x, b1.x);
-        k.ayy = make_float2(a1.y, b1.y);
-        k.azz = make_float2(a1.z, b1.z);
-        k.axy = make_float2(a1.w, b1.w);
-        k.axz = make_float2(a2.x, b2.x);
-        k.ayz = make_float2(a2.y, b2.y);
+        k[u].nmx = make_float2(-a0.x, -b0.x);
+        k[u].nmy = make_float2(-a0.y, -b0.y);
+        k[u].nmz = make_float2(-a0.z, -b0.z);
+        k[u].c2 = make_float2(live0[u] ? a0.w - cref : -INFINITY, live1[u] ? b0.w - cref : -INFINITY);
+        k[u].axx = make_float2(a1.x, b1.x);
+        k[u].ayy = make_float2(a1.y, b1.y);
+        k[u].azz = make_float2(a1.z, b1.z);
+        k[u].axy = make_float2(a1.w, b1.w);
+        k[u].axz = make_float2(a2.x, b2.x);
+        k[u].ayz = make_float2(a2.y, b2.y);
     }
-    float2 a[kMom];
+    float2 a[NP][kMom];
 #pragma unroll
-    for (int m = 0; m < kMom; ++m) a[m] = make_float2(0.f, 0.f);
+    for (int u = 0; u < NP; ++u)
+#pragma unroll
+        for (int m = 0; m < kMom; ++m) a[u][m] = make_float2(0.f, 0.f);
     double ll = 0.0, nlive = 0.0;                         // accumulated by the finishing lanes of warp sw == 0
 
     const int per = (int)(((long long)n + gridDim.x - 1) / gridDim.x);
@@ -192,17 +195,22 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
         const int gs = min(cn, g * gper), ge = min(cn, gs + gper);
         for (int b = gs; b < ge; b += PB) {
             const int np = min(PB, ge - b);
-            float2 e[PB];
+            float2 e[NP][PB];
             float sm[PB];
             // ---------------- pass 1
 #pragma unroll
             for (int p = 0; p < PB; ++p) {
                 const int ip = min(b + p, cn - 1);
                 const float4 P0 = spts[ip][0], P1 = spts[ip][1];
-                float2 dx, dy, dz;
-                const float2 q = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
-                e[p] = make_float2(ex2f(q.x), ex2f(q.y));
-                sm[p] = e[p].x + e[p].y;
+                float s = 0.f;
+#pragma unroll
+                for (int u = 0; u < NP; ++u) {
+                    float2 dx, dy, dz;
+                    const float2 q = quad2(k[u], make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
+                    e[u][p] = make_float2(ex2f(q.x), ex2f(q.y));
+                    s += e[u][p].x + e[u][p].y;
+                }
+                sm[p] = s;
             }
             reduce_scatter<PB>(sm, lane, false);
             if (rwriter) red[parity][g][ridx][sw] = sm[0];
@@ -243,10 +251,15 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
                 for (int p = 0; p < PB; ++p) {
                     const int ip = min(b + p, cn - 1);
                     const float4 P0 = spts[ip][0], P1 = spts[ip][1];
-                    float2 dx, dy, dz;
-                    const float2 q = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
-                    e[p] = q;
-                    mx[p] = fmaxf(fmaxf(q.x, q.y), kNegBig);
+                    float m = kNegBig;
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        float2 dx, dy, dz;
+                        const float2 q = quad2(k[u], make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
+                        e[u][p] = q;
+                        m = fmaxf(m, fmaxf(q.x, q.y));
+                    }
+                    mx[p] = m;
                 }
                 reduce_scatter<PB>(mx, lane, true);
                 group_bar3(1 + g, gthreads);               // everyone is done reading red[parity] (first use)
@@ -261,8 +274,13 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
 #pragma unroll
                 for (int p = 0; p < PB; ++p) {
                     const float m = finmax[g][p];
-                    e[p] = make_float2(ex2f(e[p].x - m), ex2f(e[p].y - m));
-                    sm[p] = e[p].x + e[p].y;
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        e[u][p] = make_float2(ex2f(e[u][p].x - m), ex2f(e[u][p].y - m));
+                        sacc += e[u][p].x + e[u][p].y;
+                    }
+                    sm[p] = sacc;
                 }
                 reduce_scatter<PB>(sm, lane, false);
                 if (rwriter) red[parity][g][ridx][sw] = sm[0];     // maxima were consumed before the last barrier
@@ -301,21 +319,25 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
                 const int ip = min(b + p, cn - 1);
                 const float4 P0 = spts[ip][0], P1 = spts[ip][1];
                 const float2 inv2 = fin[warp][p];
-                const float2 gam = fmul2(e[p], inv2);
-                const float2 dx = fadd2(make_float2(P0.x, P0.y), k.nmx);
-                const float2 dy = fadd2(make_float2(P0.z, P0.w), k.nmy);
-                const float2 dz = fadd2(make_float2(P1.x, P1.y), k.nmz);
-                const float2 gx = fmul2(gam, dx), gy = fmul2(gam, dy), gz = fmul2(gam, dz);
-                a[0] = fadd2(a[0], gam);
-                a[1] = fadd2(a[1], gx);
-                a[2] = fadd2(a[2], gy);
-                a[3] = fadd2(a[3], gz);
-                a[4] = ffma2(gx, dx, a[4]);
-                a[5] = ffma2(gx, dy, a[5]);
-                a[6] = ffma2(gx, dz, a[6]);
-                a[7] = ffma2(gy, dy, a[7]);
-                a[8] = ffma2(gy, dz, a[8]);
-                a[9] = ffma2(gz, dz, a[9]);
+                const float2 X = make_float2(P0.x, P0.y), Y = make_float2(P0.z, P0.w), Z = make_float2(P1.x, P1.y);
+#pragma unroll
+                for (int u = 0; u < NP; ++u) {
+                    const float2 gam = fmul2(e[u][p], inv2);
+                    const float2 dx = fadd2(X, k[u].nmx);
+                    const float2 dy = fadd2(Y, k[u].nmy);
+                    const float2 dz = fadd2(Z, k[u].nmz);
+                    const float2 gx = fmul2(gam, dx), gy = fmul2(gam, dy), gz = fmul2(gam, dz);
+                    a[u][0] = fadd2(a[u][0], gam);
+                    a[u][1] = fadd2(a[u][1], gx);
+                    a[u][2] = fadd2(a[u][2], gy);
+                    a[u][3] = fadd2(a[u][3], gz);
+                    a[u][4] = ffma2(gx, dx, a[u][4]);
+                    a[u][5] = ffma2(gx, dy, a[u][5]);
+                    a[u][6] = ffma2(gx, dz, a[u][6]);
+                    a[u][7] = ffma2(gy, dy, a[u][7]);
+                    a[u][8] = ffma2(gy, dz, a[u][8]);
+                    a[u][9] = ffma2(gz, dz, a[u][9]);
+                }
             }
             __syncwarp();                                  // fin[warp] is rewritten by the next batch's finishing lanes
             parity ^= 1;
@@ -324,15 +346,18 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
     // ---- partial rows: partial[row][m][Jp], row = blockIdx * G + g
     const size_t row = (size_t)blockIdx.x * G + g;
     float* dst = partial + row * (size_t)kMom * Jp;
-    if (live0) {
-        const int j = sw * 32 + lane;
 #pragma unroll
-        for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].x;
-    }
-    if (live1) {
-        const int j = (sw + Sdiv) * 32 + lane;
+    for (int u = 0; u < NP; ++u) {
+        if (live0[u]) {
+            const int j = (sw + (2 * u) * Sdiv) * 32 + lane;
 #pragma unroll
-        for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].y;
+            for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[u][m].x;
+        }
+        if (live1[u]) {
+            const int j = (sw + (2 * u + 1) * Sdiv) * 32 + lane;
+#pragma unroll
+            for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[u][m].y;
+        }
     }
     if (sw == 0) {
 #pragma unroll
@@ -381,6 +406,13 @@ static int occ_blocks(K kern, int threads) {
 
 // (Sdiv, G, W, grid, big) for the packed kernel; requires S = Jp/32 >= 2
 void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdiv, int* G, int* grid, int* big) {
+    if (one_cta_per_sm == 3 && Jp / 32 >= 17) {          // two teams of ceil(S/4) warps, 4 components per lane
+        const int S4 = Jp / 32;
+        const int sd = (S4 + 3) / 4;
+        *W = 2 * sd; *Sdiv = sd; *G = 2; *big = 2;
+        *grid = num_sms;
+        return;
+    }
     const int S = Jp / 32;
     const int sdiv = (S + 1) / 2;                   // warps per group: each warp owns slots sw and sw + sdiv
     int g = 1;
@@ -390,7 +422,7 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
     // 72-register CTAs (71.5 vs 77.6 us on configs[1]); smaller CTAs co-reside 2-4 per SM.  one_cta_per_sm == 1 forces
     // the register-rich build, == 2 the two-CTA build (profiling switches).
     *big = (one_cta_per_sm == 1 || (one_cta_per_sm == 0 && w >= 8) || w > 13) ? 1 : 0;
-    int occ = *big ? occ_blocks(em_flat3_kernel<512, 1, 8>, w * 32) : occ_blocks(em_flat3_kernel<416, 2, 4>, w * 32);
+    int occ = *big ? occ_blocks(em_flat3_kernel<512, 1, 8, 1>, w * 32) : occ_blocks(em_flat3_kernel<416, 2, 4, 1>, w * 32);
     if (occ > 4) occ = 4;
     if (w >= 8 && occ > 2) occ = 2;
     int ctas = occ * num_sms;
@@ -405,11 +437,14 @@ cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int 
                             cudaStream_t s) {
     const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
     const int ncref = (m.Jp + 127) / 128;
-    if (big)
-        em_flat3_kernel<512, 1, 8><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
+    if (big == 2)
+        em_flat3_kernel<448, 1, 8, 2><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
+                                                            done_flag, eps_on);
+    else if (big)
+        em_flat3_kernel<512, 1, 8, 1><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
                                                        done_flag, eps_on);
     else
-        em_flat3_kernel<416, 2, 4><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
+        em_flat3_kernel<416, 2, 4, 1><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
                                                        done_flag, eps_on);
     return cudaGetLastError();
 }
