@@ -406,7 +406,7 @@ static int occ_blocks(K kern, int threads) {
 
 // (Sdiv, G, W, grid, big) for the packed kernel; requires S = Jp/32 >= 2
 void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdiv, int* G, int* grid, int* big) {
-    if (one_cta_per_sm == 3 && Jp / 32 >= 17) {          // two teams of ceil(S/4) warps, 4 components per lane
+    if (one_cta_per_sm == 3 && Jp / 32 >= 17 && (Jp / 32 + 3) / 4 <= 7) {          // two teams of ceil(S/4) warps, 4 components per lane
         const int S4 = Jp / 32;
         const int sd = (S4 + 3) / 4;
         *W = 2 * sd; *Sdiv = sd; *G = 2; *big = 2;
@@ -438,7 +438,7 @@ cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int 
     const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
     const int ncref = (m.Jp + 127) / 128;
     if (big == 2)
-        em_flat3_kernel<448, 1, 8, 2><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
+        em_flat3_kernel<448, 1, 4, 2><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
                                                             done_flag, eps_on);
     else if (big)
         em_flat3_kernel<512, 1, 8, 1><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
