@@ -323,7 +323,7 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     m.J = J; m.Jp = Jp; m.cov_type = cfg->cov_type; m.flavor = cfg->flavor; m.sigma_bug = cfg->sigma_bug; m.tol = cfg->tol;
     m.means = ctx->f_means.as<float>(); m.covs = ctx->f_covs.as<float>(); m.weights = ctx->f_weights.as<float>();
     m.inv_cov = ctx->f_invcov.as<float>(); m.packed = ctx->f_packed.as<PackedComp>();
-    CK(ctx->cref.ensure((size_t)(Jp / 128 + 2) * sizeof(float)));
+    CK(ctx->cref.ensure((size_t)(Jp / 32 + 4) * sizeof(float)));
     m.cref_blocks = ctx->cref.as<float>();
     cudaStream_t s = ctx->stream;
     CK(cudaMemcpyAsync(m.means, init_means, (size_t)J * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -375,6 +375,12 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
                 CK(launch_em_flat2(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, m.cref_blocks, JT, W, Sdiv,
                                    G, grid, big, ctx->partial.as<float>(), ctx->rowaux.as<double>(), done_at + it, s));
             if (prof) CK(cudaEventRecord(ctx->pev[2 * it + 1], s));
+            if (ctx->nranks <= 1 && cfg->reserved != 3) {      // single GPU: reduce + finalize in one kernel
+                launch_flat_reduce_finalize(m, ctx->partial.as<float>(), ctx->rowaux.as<double>(), grid * G, ctx->ctrl.as<int>(),
+                                            done_at, it, ctx->hist.as<double>(), (double)ctx->n_total, s);
+                ctx->launches += 2;
+                continue;
+            }
             CK(launch_flat_reduce(ctx->partial.as<float>(), ctx->rowaux.as<double>(), grid * G, m, ctx->acc.as<double>(),
                                   done_at + it, s));
             ctx->launches += 2;

@@ -65,15 +65,13 @@ __device__ __forceinline__ PackedComp pack_diag(double logw, double mx, double m
 
 // One thread per (padded) component: model arrays -> PackedComp.  first=1 reproduces
 // gmm_impl.py:122 (inv_cov = 1/sqrt(cov) before the loop), otherwise :134.
-// max of c2 over the (128-thread) block -> cref_blocks[blockIdx.x]; every thread of the block must call it
-__device__ __forceinline__ void block_max_c2(float c2, float* __restrict__ cref_blocks) {
-    __shared__ float s_c2[4];
+// max of c2 over each warp's 32 components -> cref_blocks[slot]; every thread of the warp must call it
+__device__ __forceinline__ void block_max_c2(float c2, float* __restrict__ cref_blocks, int n_slots) {
     float v = c2;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if ((threadIdx.x & 31) == 0) s_c2[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) cref_blocks[blockIdx.x] = fmaxf(fmaxf(s_c2[0], s_c2[1]), fmaxf(s_c2[2], s_c2[3]));
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if ((threadIdx.x & 31) == 0 && slot < n_slots) cref_blocks[slot] = v;
 }
 
 __global__ void __launch_bounds__(128) flat_pack_kernel(FlatModel m, int first) {
@@ -98,7 +96,7 @@ __global__ void __launch_bounds__(128) flat_pack_kernel(FlatModel m, int first) 
         }
     }
     if (j < m.Jp) m.packed[j] = p;
-    block_max_c2(p.c2, m.cref_blocks);       // single convergent call site: full-mask shuffles + __syncthreads inside
+    block_max_c2(p.c2, m.cref_blocks, m.Jp >> 5);       // single convergent call site: full-mask shuffles inside
 }
 
 // ------------------------------------------------------------------------------------------
@@ -292,82 +290,147 @@ __global__ void __launch_bounds__(256) em_flat_kernel(const float* __restrict__ 
 // done_at[it] is written only by iteration it-1 (block 0), so every kernel of iteration `it` reads a
 // settled flag; acc[0] = sum log-lik, acc[1] = number of live points (= sum_j N_j), set before this runs.
 // ------------------------------------------------------------------------------------------
+// moments of one component (fp64, centred on the old mean) -> new parameters, re-packed; returns the new c2
+__device__ __forceinline__ float finalize_component(const FlatModel& m, int j, const double* A, double total, double n_total) {
+    const double M0 = A[0];
+    const double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
+    PackedComp p;
+    if (m.flavor == HGMM_FLAVOR_PY) {
+        // gmm_impl.py:81-103 with S1 = sum g x, S2 = sum g x^2 rebuilt from the centred moments
+        const double nk = M0 + 1e-8;
+        const double S1[3] = {A[1] + mx * M0, A[2] + my * M0, A[3] + mz * M0};
+        const double mu0[3] = {mx, my, mz};
+        const double M2d[3] = {A[4], A[7], A[9]};
+        double mean[3], cov[3], iv[3];
+        for (int d = 0; d < 3; ++d) {
+            mean[d] = S1[d] / nk;
+            const double S2 = M2d[d] + 2.0 * mu0[d] * A[1 + d] + mu0[d] * mu0[d] * M0;
+            cov[d] = S2 / nk - 2.0 * mean[d] * S1[d] / nk + mean[d] * mean[d] + 1e-6;
+        }
+        if (m.cov_type == HGMM_COV_SPHERICAL) {
+            const double c = (cov[0] + cov[1] + cov[2]) / 3.0;
+            cov[0] = cov[1] = cov[2] = c;
+            m.covs[j] = (float)c;
+        } else {
+            m.covs[3 * j] = (float)cov[0]; m.covs[3 * j + 1] = (float)cov[1]; m.covs[3 * j + 2] = (float)cov[2];
+        }
+        for (int d = 0; d < 3; ++d) iv[d] = 1.0 / (sqrt(cov[d] + 1e-6) + 1e-8);
+        if (m.cov_type == HGMM_COV_SPHERICAL) m.inv_cov[j] = (float)iv[0];
+        else { m.inv_cov[3 * j] = (float)iv[0]; m.inv_cov[3 * j + 1] = (float)iv[1]; m.inv_cov[3 * j + 2] = (float)iv[2]; }
+        const double w = nk / n_total;
+        m.weights[j] = (float)w;
+        m.means[3 * j] = (float)mean[0]; m.means[3 * j + 1] = (float)mean[1]; m.means[3 * j + 2] = (float)mean[2];
+        p = pack_diag(log((double)(float)w + 1e-8), (float)mean[0], (float)mean[1], (float)mean[2], iv[0], iv[1], iv[2], 3);
+    } else {
+        // gmm_kernels.cu:156-210: pi = N_j / sum N_k; mu = weighted mean; Sigma centred on the NEW mu
+        if (M0 > 0.0) {
+            const double r = 1.0 / M0;
+            const double dx = A[1] * r, dy = A[2] * r, dz = A[3] * r;
+            Sym3 s{A[4] * r - dx * dx, A[5] * r - dx * dy, A[6] * r - dx * dz, A[7] * r - dy * dy, A[8] * r - dy * dz,
+                   A[9] * r - dz * dz};
+            const double w = M0 / total;
+            const float fmx = (float)(mx + dx), fmy = (float)(my + dy), fmz = (float)(mz + dz);
+            m.means[3 * j] = fmx; m.means[3 * j + 1] = fmy; m.means[3 * j + 2] = fmz;
+            float* c = m.covs + 9 * j;
+            c[0] = (float)s.xx; c[1] = c[3] = (float)s.xy; c[2] = c[6] = (float)s.xz;
+            c[4] = (float)s.yy; c[5] = c[7] = (float)s.yz; c[8] = (float)s.zz;
+            m.weights[j] = (float)w;
+            p = pack_full(log(w), fmx, fmy, fmz, s, m.sigma_bug != 0, 0.0);
+        } else {
+            // the reference divides 0/0 here; the engine retires the component instead
+            m.weights[j] = 0.f;
+            p = pack_full(-INFINITY, mx, my, mz, Sym3{1, 0, 0, 1, 0, 1}, false, 0.0);
+        }
+    }
+    m.packed[j] = p;
+    return p.c2;
+}
+
+// stopping rule + bookkeeping of iteration `it` (one thread of the grid)
+__device__ __forceinline__ void finalize_bookkeeping(const FlatModel& m, double ll_sum, int* ctrl, int* done_at, int it,
+                                                     double* ll_hist, double n_total) {
+    const double ll = (m.flavor == HGMM_FLAVOR_PY) ? ll_sum / n_total : ll_sum;
+    ll_hist[it] = ll;
+    const bool conv = (m.flavor == HGMM_FLAVOR_PY) && it > 0 && fabs(ll - ll_hist[it - 1]) < (double)m.tol;
+    done_at[it + 1] = conv ? 1 : 0;
+    ctrl[1] = it + 1;
+    ctrl[0] = conv ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(128) flat_finalize_kernel(FlatModel m, const double* __restrict__ acc, int* __restrict__ ctrl,
                                                             int* __restrict__ done_at, int it, double* __restrict__ ll_hist,
                                                             double n_total) {
     const bool done = done_at[it] != 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (done) {
-            done_at[it + 1] = 1;
-        } else {
-            const double ll = (m.flavor == HGMM_FLAVOR_PY) ? acc[0] / n_total : acc[0];
-            ll_hist[it] = ll;
-            const bool conv = (m.flavor == HGMM_FLAVOR_PY) && it > 0 && fabs(ll - ll_hist[it - 1]) < (double)m.tol;
-            done_at[it + 1] = conv ? 1 : 0;
-            ctrl[1] = it + 1;
-            ctrl[0] = conv ? 1 : 0;
-        }
+        if (done) done_at[it + 1] = 1;
+        else finalize_bookkeeping(m, acc[0], ctrl, done_at, it, ll_hist, n_total);
     }
     if (done) return;
     const double total = acc[1];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     float my_c2 = -INFINITY;
-    if (j < m.J) {
-        const double* A = acc + kAccHdr + (size_t)j * kMom;
-        const double M0 = A[0];
-        const double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
-        PackedComp p;
-        if (m.flavor == HGMM_FLAVOR_PY) {
-            // gmm_impl.py:81-103 with S1 = sum g x, S2 = sum g x^2 rebuilt from the centred moments
-            const double nk = M0 + 1e-8;
-            const double S1[3] = {A[1] + mx * M0, A[2] + my * M0, A[3] + mz * M0};
-            const double mu0[3] = {mx, my, mz};
-            const double M2d[3] = {A[4], A[7], A[9]};
-            double mean[3], cov[3], iv[3];
-            for (int d = 0; d < 3; ++d) {
-                mean[d] = S1[d] / nk;
-                const double S2 = M2d[d] + 2.0 * mu0[d] * A[1 + d] + mu0[d] * mu0[d] * M0;
-                cov[d] = S2 / nk - 2.0 * mean[d] * S1[d] / nk + mean[d] * mean[d] + 1e-6;
-            }
-            if (m.cov_type == HGMM_COV_SPHERICAL) {
-                const double c = (cov[0] + cov[1] + cov[2]) / 3.0;
-                cov[0] = cov[1] = cov[2] = c;
-                m.covs[j] = (float)c;
-            } else {
-                m.covs[3 * j] = (float)cov[0]; m.covs[3 * j + 1] = (float)cov[1]; m.covs[3 * j + 2] = (float)cov[2];
-            }
-            for (int d = 0; d < 3; ++d) iv[d] = 1.0 / (sqrt(cov[d] + 1e-6) + 1e-8);
-            if (m.cov_type == HGMM_COV_SPHERICAL) m.inv_cov[j] = (float)iv[0];
-            else { m.inv_cov[3 * j] = (float)iv[0]; m.inv_cov[3 * j + 1] = (float)iv[1]; m.inv_cov[3 * j + 2] = (float)iv[2]; }
-            const double w = nk / n_total;
-            m.weights[j] = (float)w;
-            m.means[3 * j] = (float)mean[0]; m.means[3 * j + 1] = (float)mean[1]; m.means[3 * j + 2] = (float)mean[2];
-            p = pack_diag(log((double)(float)w + 1e-8), (float)mean[0], (float)mean[1], (float)mean[2], iv[0], iv[1], iv[2], 3);
-        } else {
-            // gmm_kernels.cu:156-210: pi = N_j / sum N_k; mu = weighted mean; Sigma centred on the NEW mu
-            if (M0 > 0.0) {
-                const double r = 1.0 / M0;
-                const double dx = A[1] * r, dy = A[2] * r, dz = A[3] * r;
-                Sym3 s{A[4] * r - dx * dx, A[5] * r - dx * dy, A[6] * r - dx * dz, A[7] * r - dy * dy, A[8] * r - dy * dz,
-                       A[9] * r - dz * dz};
-                const double w = M0 / total;
-                const float fmx = (float)(mx + dx), fmy = (float)(my + dy), fmz = (float)(mz + dz);
-                m.means[3 * j] = fmx; m.means[3 * j + 1] = fmy; m.means[3 * j + 2] = fmz;
-                float* c = m.covs + 9 * j;
-                c[0] = (float)s.xx; c[1] = c[3] = (float)s.xy; c[2] = c[6] = (float)s.xz;
-                c[4] = (float)s.yy; c[5] = c[7] = (float)s.yz; c[8] = (float)s.zz;
-                m.weights[j] = (float)w;
-                p = pack_full(log(w), fmx, fmy, fmz, s, m.sigma_bug != 0, 0.0);
-            } else {
-                // the reference divides 0/0 here; the engine retires the component instead
-                m.weights[j] = 0.f;
-                p = pack_full(-INFINITY, mx, my, mz, Sym3{1, 0, 0, 1, 0, 1}, false, 0.0);
-            }
-        }
-        m.packed[j] = p;
-        my_c2 = p.c2;
+    if (j < m.J) my_c2 = finalize_component(m, j, acc + kAccHdr + (size_t)j * kMom, total, n_total);
+    block_max_c2(my_c2, m.cref_blocks, m.Jp >> 5);
+}
+
+// Single-GPU fusion of flat_reduce_kernel + flat_finalize_kernel: one CTA per 32-component slot, 32 warps.
+// warp w < 30: moment w % 10, row group w / 10 of 3; warp 30: sum of log-lik / live counts; then lanes of warp 0
+// finalize their component.  cref_blocks gets one entry per slot (n_cref = Jp / 32 in this mode).
+__global__ void __launch_bounds__(1024) flat_reduce_finalize_kernel(FlatModel m, const float* __restrict__ partial,
+                                                                    const double* __restrict__ rowaux, int rows,
+                                                                    int* __restrict__ ctrl, int* __restrict__ done_at, int it,
+                                                                    double* __restrict__ ll_hist, double n_total) {
+    const bool done = done_at[it] != 0;
+    if (done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) done_at[it + 1] = 1;
+        return;
     }
-    block_max_c2(my_c2, m.cref_blocks);
+    __shared__ double sm[3][kMom][33];
+    __shared__ double s_aux[2];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    if (w < 30) {
+        const int k = w % kMom, rg = w / kMom;
+        const float* src = partial + (size_t)k * m.Jp + j;
+        const size_t stride = (size_t)kMom * m.Jp;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        int r = rg;
+        for (; r + 9 < rows; r += 12) {
+            v0 += (double)src[(size_t)r * stride];
+            v1 += (double)src[(size_t)(r + 3) * stride];
+            v2 += (double)src[(size_t)(r + 6) * stride];
+            v3 += (double)src[(size_t)(r + 9) * stride];
+        }
+        for (; r < rows; r += 3) v0 += (double)src[(size_t)r * stride];
+        sm[rg][k][lane] = (v0 + v1) + (v2 + v3);
+    } else if (w == 30) {
+        double l = 0.0, c = 0.0;
+        for (int q = lane; q < rows; q += 32) {
+            l += rowaux[2 * q];
+            c += rowaux[2 * q + 1];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            l += __shfl_xor_sync(0xffffffffu, l, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if (lane == 0) {
+            s_aux[0] = l;
+            s_aux[1] = c;
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        double A[kMom];
+#pragma unroll
+        for (int k = 0; k < kMom; ++k) A[k] = (sm[0][k][lane] + sm[1][k][lane]) + sm[2][k][lane];
+        float my_c2 = -INFINITY;
+        if (j < m.J) my_c2 = finalize_component(m, j, A, s_aux[1], n_total);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_c2 = fmaxf(my_c2, __shfl_xor_sync(0xffffffffu, my_c2, o));
+        if (lane == 0) m.cref_blocks[blockIdx.x] = my_c2;
+        if (blockIdx.x == 0 && lane == 0) finalize_bookkeeping(m, s_aux[0], ctrl, done_at, it, ll_hist, n_total);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -504,6 +567,11 @@ void launch_aos_to_soa_transform(const float* xyz, int64_t n, const double* Rt, 
 void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s) {
     flat_pack_kernel<<<(m.Jp + 127) / 128, 128, 0, s>>>(m, first);
 }
+void launch_flat_reduce_finalize(const FlatModel& m, const float* partial, const double* rowaux, int rows, int* ctrl, int* done_at,
+                                 int it, double* ll_hist, double n_total, cudaStream_t s) {
+    flat_reduce_finalize_kernel<<<m.Jp / 32, 1024, 0, s>>>(m, partial, rowaux, rows, ctrl, done_at, it, ll_hist, n_total);
+}
+
 void launch_flat_finalize(const FlatModel& m, const double* acc, int* ctrl, int* done_at, int it, double* ll_hist, double n_total,
                           cudaStream_t s) {
     flat_finalize_kernel<<<(m.J + 127) / 128, 128, 0, s>>>(m, acc, ctrl, done_at, it, ll_hist, n_total);

@@ -368,7 +368,7 @@ cudaError_t launch_em_flat2(const float* x, const float* y, const float* z, int 
                             int JT, int W, int Sdiv, int G, int grid, int big, float* partial, double* rowaux,
                             const int* done_flag, cudaStream_t s) {
     const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
-    const int ncref = (m.Jp + 127) / 128;
+    const int ncref = m.Jp / 32;
     const int th = W * 32;
 #define HGMM_LAUNCH2(JTV, MAXT, MINB)                                                                                       \
     em_flat2_kernel<JTV, MAXT, MINB><<<grid, th, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, \

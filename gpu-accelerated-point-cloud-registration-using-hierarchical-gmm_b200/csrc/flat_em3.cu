@@ -436,7 +436,7 @@ cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int 
                             int W, int Sdiv, int G, int grid, int big, float* partial, double* rowaux, const int* done_flag,
                             cudaStream_t s) {
     const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
-    const int ncref = (m.Jp + 127) / 128;
+    const int ncref = m.Jp / 32;
     if (big == 2)
         em_flat3_kernel<448, 1, 4, 2><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
                                                             done_flag, eps_on);

@@ -19,7 +19,7 @@ struct FlatModel {
     float* weights;            // [Jp]
     float* inv_cov;            // PY flavour: 1/std, [Jp,3] | [Jp]
     PackedComp* packed;        // [Jp]
-    float* cref_blocks;        // [ceil(Jp/128)] max c2 of each block of 128 components (reference for the sweep)
+    float* cref_blocks;        // [Jp/32] max c2 of each 32-component slot (the sweep's fixed reference is their maximum)
 };
 
 struct TreeModel {
@@ -49,6 +49,8 @@ void launch_aos_to_soa_transform(const float* xyz, int64_t n, const double* Rt, 
 void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s);
 void launch_flat_finalize(const FlatModel& m, const double* acc, int* ctrl, int* done_at, int it, double* ll_hist, double n_total,
                           cudaStream_t s);
+void launch_flat_reduce_finalize(const FlatModel& m, const float* partial, const double* rowaux, int rows, int* ctrl, int* done_at,
+                                 int it, double* ll_hist, double n_total, cudaStream_t s);
 // flat_em2.cu
 void flat2_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* JT, int* W, int* Sdiv, int* G, int* grid, int* big);
 cudaError_t launch_em_flat2(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,

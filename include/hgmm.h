@@ -72,7 +72,7 @@ typedef struct hgmm_flat_config {
     float tol;                     /* PY flavour: stop when |d mean-log-lik| < tol; CPP flavour ignores it */
     int32_t sigma_bug;             /* CPP flavour only: reproduce gmm_kernels.cu:97-103 (d^T Sigma d) */
     int32_t tile_points;           /* 0 = auto; points per CTA tile (64,128,256,512) */
-    int32_t reserved;              /* kernel variant: 0 = default (packed-FP32 sweep), 1 = first-generation two-phase kernel, 2 = scalar single-evaluation kernel */
+    int32_t reserved;              /* kernel variant: 0 = default (packed-FP32 sweep), 1 = first-generation two-phase kernel, 2 = scalar single-evaluation kernel, 3 = packed sweep with separate reduce / finalize launches */
 } hgmm_flat_config;
 
 typedef struct hgmm_tree_config {

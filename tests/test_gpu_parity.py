@@ -94,7 +94,7 @@ def test_flat_full_config2_matches_c_oracle(engine, bun000, J, sig):
         assert max(errs) < TOL, errs
 
 
-@pytest.mark.parametrize("variant,tile", [(0, 0), (0, 1), (0, 2), (0, 3), (2, 0), (2, 1), (1, 64), (1, 128), (1, 256), (1, 512)])
+@pytest.mark.parametrize("variant,tile", [(0, 0), (0, 1), (0, 2), (0, 3), (3, 0), (2, 0), (2, 1), (1, 64), (1, 128), (1, 256), (1, 512)])
 def test_flat_kernel_variants_agree(engine, bun000, variant, tile):
     from oracle import flat_gmm
     X = bun000[::5]
