@@ -479,9 +479,10 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
     cudaStream_t s = ctx->stream;
     int chunk = cfg->chunk_points;
     if (chunk <= 0) {
-        chunk = (int)(((int64_t)n / ((int64_t)ctx->num_sms * 16) + 31) / 32 * 32);
-        if (chunk < 128) chunk = 128;
-        if (chunk > 1024) chunk = 1024;
+        // one warp per chunk: aim at ~32 chunk-warps per SM; tiny clouds are latency-bound, so the floor is one point per lane
+        chunk = (int)(((int64_t)n / ((int64_t)ctx->num_sms * 32) + 31) / 32 * 32);
+        if (chunk < 32) chunk = 32;
+        if (chunk > 512) chunk = 512;
     }
     if (chunk % 32 != 0 || chunk > 65536) FAIL(HGMM_ERR_INVALID, "chunk_points must be a multiple of 32");
     const int max_iters = cfg->max_iters_per_level > 0 ? cfg->max_iters_per_level : 10000;
@@ -540,31 +541,36 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
 
     int cur = 0;
     int64_t n_parents = 1;
-    const int batch = 4;      // iterations enqueued between polls of the control word (no-ops once converged)
+    const int batch = 8;      // iterations enqueued between polls of the control word (no-ops once converged)
+    const bool fast_ll = cfg->ll_mode == HGMM_LL_ESTEP;
+    CK(ctx->done_at.ensure((size_t)(max_iters + batch + 4) * sizeof(int)));
+    int* done_at = ctx->done_at.as<int>();
     for (int l = 0; l < L; ++l) {
         CK(cudaMemsetAsync(ctrl, 0, 8 * sizeof(int), s));
         CK(cudaMemsetAsync(qstate, 0, 4 * sizeof(double), s));
+        CK(cudaMemsetAsync(done_at, 0, (size_t)(max_iters + batch + 4) * sizeof(int), s));
         const int64_t cnt = level_count_h(l);
         const int chunks_bound = (int)((n + chunk - 1) / chunk + (l == 0 ? 0 : cnt / 8));
         const PackedComp* level_packed = t.packed + level_base_h(l);
         bool done = false;
+        int it = 0;
         while (!done) {
-            for (int b = 0; b < batch; ++b) {
-                CK(launch_tree_estep(w[cur], t, l, acc, chunks_bound, nchunks_dev, ctrl, s));
+            for (int b = 0; b < batch; ++b, ++it) {
+                CK(launch_tree_estep(w[cur], t, l, acc, chunks_bound, nchunks_dev, done_at + it, cfg->reserved == 1, s));
                 r = allreduce(ctx, acc, kAccHdr + (size_t)cnt * kMom);
                 if (r != HGMM_OK) return r;
-                launch_tree_mstep(t, l, acc, (double)ctx->n_total, cfg->ld, ctrl, s);
+                launch_tree_mstep(t, l, acc, (double)ctx->n_total, cfg->ld, ctrl, done_at, it, fast_ll ? 1 : 0, qstate, cfg->ls,
+                                  max_iters, s);
                 ctx->launches += 2;
-                if (cfg->ll_mode == HGMM_LL_LEVEL) {
-                    launch_tree_zero_ll(acc, ctrl, s);
+                if (!fast_ll) {
+                    launch_tree_zero_ll(acc, done_at + it, s);
                     CK(launch_level_ll(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), n, level_packed, (int)cnt, acc,
-                                       ctx->num_sms, s));
-                    ctx->launches += 2;
+                                       done_at + it, ctx->num_sms, s));
                     r = allreduce(ctx, acc, 1);
                     if (r != HGMM_OK) return r;
+                    launch_tree_converge(acc, ctrl, done_at, it, qstate, cfg->ls, max_iters, s);
+                    ctx->launches += 3;
                 }
-                launch_tree_converge(acc, ctrl, qstate, cfg->ls, max_iters, s);
-                ctx->launches += 1;
             }
             CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
@@ -583,6 +589,8 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
             n_parents *= 8;
         }
     }
+    launch_tree_cplx(t, s);
+    ctx->launches += 1;
     if (out_current) {
         CK(ctx->current.ensure((size_t)n * sizeof(int64_t)));
         launch_tree_current(w[cur], n, L - 1, ctx->current.as<int64_t>(), s);

@@ -443,7 +443,9 @@ template <int MODE>
 __global__ void __launch_bounds__(256) scan_components_kernel(const float* __restrict__ px, const float* __restrict__ py,
                                                               const float* __restrict__ pz, int n,
                                                               const PackedComp* __restrict__ packed, int Jp,
-                                                              int32_t* __restrict__ labels, double* __restrict__ acc) {
+                                                              int32_t* __restrict__ labels, double* __restrict__ acc,
+                                                              const int* __restrict__ done_flag) {
+    if (done_flag && *done_flag) return;
     __shared__ __align__(16) PackedComp sp[kStage];
     __shared__ uint64_t bar;
     __shared__ double s_ll[8];
@@ -638,16 +640,16 @@ cudaError_t launch_predict(const float* x, const float* y, const float* z, int n
     if (n <= 0) return cudaSuccess;
     int work = ((n + 1) / 2 + 255) / 256;
     int grid = work < num_sms * 4 ? work : num_sms * 4;
-    scan_components_kernel<0><<<grid, 256, 0, s>>>(x, y, z, n, packed, Jp, labels, nullptr);
+    scan_components_kernel<0><<<grid, 256, 0, s>>>(x, y, z, n, packed, Jp, labels, nullptr, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_level_ll(const float* x, const float* y, const float* z, int n, const PackedComp* packed, int Jp,
-                            double* acc, int num_sms, cudaStream_t s) {
+                            double* acc, const int* done_flag, int num_sms, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     int work = ((n + 1) / 2 + 255) / 256;
     int grid = work < num_sms * 4 ? work : num_sms * 4;
-    scan_components_kernel<1><<<grid, 256, 0, s>>>(x, y, z, n, packed, Jp, nullptr, acc);
+    scan_components_kernel<1><<<grid, 256, 0, s>>>(x, y, z, n, packed, Jp, nullptr, acc, done_flag);
     return cudaGetLastError();
 }
 

@@ -64,7 +64,7 @@ cudaError_t launch_em_flat(const float* x, const float* y, const float* z, int n
 cudaError_t launch_predict(const float* x, const float* y, const float* z, int n, const PackedComp* packed, int Jp,
                            int32_t* labels, int num_sms, cudaStream_t s);
 cudaError_t launch_level_ll(const float* x, const float* y, const float* z, int n, const PackedComp* packed, int Jp,
-                            double* acc, int num_sms, cudaStream_t s);
+                            double* acc, const int* done_flag, int num_sms, cudaStream_t s);
 cudaError_t launch_ffma_peak(float* out, int blocks, int iters, int mode, cudaStream_t s);
 
 // flat_em3.cu (packed FP32)
@@ -78,10 +78,12 @@ cudaError_t launch_ffma2_peak(float* out, int blocks, int iters, cudaStream_t s)
 void launch_tree_init(const TreeModel& t, const float* init_means, float sig2, cudaStream_t s);
 void launch_tree_pack_all(const TreeModel& t, cudaStream_t s);
 cudaError_t launch_tree_estep(const TreeWork& w, const TreeModel& t, int level, double* acc, int n_chunks_bound,
-                              const int* n_chunks_dev, const int* ctrl, cudaStream_t s);
-void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_total, float ld, const int* ctrl, cudaStream_t s);
-void launch_tree_converge(double* acc, int* ctrl, double* qstate, float ls, int max_iters, cudaStream_t s);
-void launch_tree_zero_ll(double* acc, const int* ctrl, cudaStream_t s);
+                              const int* n_chunks_dev, const int* done_flag, int scalar_variant, cudaStream_t s);
+void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_total, float ld, int* ctrl, int* done_at, int it,
+                       int merge_converge, double* qstate, float ls, int max_iters, cudaStream_t s);
+void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, cudaStream_t s);
+void launch_tree_zero_ll(double* acc, const int* done_flag, cudaStream_t s);
+void launch_tree_cplx(const TreeModel& t, cudaStream_t s);
 void launch_tree_current(const TreeWork& w, int n, int level, int64_t* current, cudaStream_t s);
 void launch_iota(int* p, int n, cudaStream_t s);
 

@@ -17,60 +17,92 @@ constexpr int kRegMom = 10;     // M0, M1(3), raw M2 (xx xy xz yy yz zz) -- fp64
 // ------------------------------------------------------------------------------------------
 // E-step: one thread per target point, greedy root->leaf descent
 // ------------------------------------------------------------------------------------------
+constexpr int kTopNodes = 72;       // levels 0 and 1 (8 + 64 nodes): accumulated per CTA in shared memory
+
 __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict__ tx, const float* __restrict__ ty,
                                                         const float* __restrict__ tz, int n, const double* __restrict__ Rt,
                                                         const PackedComp* __restrict__ packed, const float* __restrict__ cplx,
                                                         int L, float lambda_c, double* __restrict__ racc, int want_m2,
                                                         const int* __restrict__ ctrl) {
     if (ctrl[0]) return;
+    // Every point visits level 0 and most visit level 1, i.e. 40k points land on 8 + 64 addresses: those two levels
+    // are summed per CTA with native fp32 shared-memory atomics (<= 256 terms) and flushed as one fp64 atomic per
+    // touched slot; deeper levels (>= 512 nodes) go straight to fp64 global atomics.
+    __shared__ float s_top[kTopNodes][kRegMom];
+    for (int k = threadIdx.x; k < kTopNodes * kRegMom; k += blockDim.x) (&s_top[0][0])[k] = 0.f;
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float x, y, z;
-    {
-        const double a = tx[i], b = ty[i], c = tz[i];      // t_target = target R^T + t  (hgmm_gpu.py:757,613-614)
-        x = (float)(Rt[0] * a + Rt[1] * b + Rt[2] * c + Rt[9]);
-        y = (float)(Rt[3] * a + Rt[4] * b + Rt[5] * c + Rt[10]);
-        z = (float)(Rt[6] * a + Rt[7] * b + Rt[8] * c + Rt[11]);
-    }
-    int j0 = 0;                                             // child(-1) = 0
-    for (int l = 0; l < L; ++l) {
-        const float4* c4 = reinterpret_cast<const float4*>(packed + j0);
-        float q[8];
-        float m = kNegBig;
-        int best = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float4 p0 = __ldg(c4 + 3 * k), p1 = __ldg(c4 + 3 * k + 1);
-            const float4 p2 = __ldg(c4 + 3 * k + 2);
-            float dx, dy, dz;
-            q[k] = quad_q2(p0, p1, make_float2(p2.x, p2.y), x, y, z, dx, dy, dz);
-            if (q[k] > m) { m = q[k]; best = k; }
+    if (i < n) {
+        float x, y, z;
+        {
+            const double a = tx[i], b = ty[i], c = tz[i];      // t_target = target R^T + t  (hgmm_gpu.py:757,613-614)
+            x = (float)(Rt[0] * a + Rt[1] * b + Rt[2] * c + Rt[9]);
+            y = (float)(Rt[3] * a + Rt[4] * b + Rt[5] * c + Rt[10]);
+            z = (float)(Rt[6] * a + Rt[7] * b + Rt[8] * c + Rt[11]);
         }
-        float s = 0.f;
+        int j0 = 0;                                             // child(-1) = 0
+        for (int l = 0; l < L; ++l) {
+            const float4* c4 = reinterpret_cast<const float4*>(packed + j0);
+            float q[8];
+            float m = kNegBig;
+            int best = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += ex2f(q[k] - m);
-        const float lse2 = m + lg2f(s);
-        const bool alive = lse2 > kLog2Eps15;               // den > eps else gamma = zeros (:563-567)
-        const int sid = j0 + (alive ? best : 0);
-        if (cplx[sid] <= lambda_c) break;                   // :572-573, before accumulating
-        const float gam = alive ? 1.0f / s : 0.f;           // gamma of the arg-max child
-        if (gam >= 1e-15f) {                                // accumulate() guard (:457-459)
-            double* A = racc + (size_t)sid * kRegMom;
-            const double g = gam, X = x, Y = y, Z = z;
-            atomicAdd(A + 0, g);
-            atomicAdd(A + 1, g * X);
-            atomicAdd(A + 2, g * Y);
-            atomicAdd(A + 3, g * Z);
-            if (want_m2) {
-                atomicAdd(A + 4, g * X * X);
-                atomicAdd(A + 5, g * X * Y);
-                atomicAdd(A + 6, g * X * Z);
-                atomicAdd(A + 7, g * Y * Y);
-                atomicAdd(A + 8, g * Y * Z);
-                atomicAdd(A + 9, g * Z * Z);
+            for (int k = 0; k < 8; ++k) {
+                const float4 p0 = __ldg(c4 + 3 * k), p1 = __ldg(c4 + 3 * k + 1);
+                const float4 p2 = __ldg(c4 + 3 * k + 2);
+                float dx, dy, dz;
+                q[k] = quad_q2(p0, p1, make_float2(p2.x, p2.y), x, y, z, dx, dy, dz);
+                if (q[k] > m) { m = q[k]; best = k; }
             }
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += ex2f(q[k] - m);
+            const float lse2 = m + lg2f(s);
+            const bool alive = lse2 > kLog2Eps15;               // den > eps else gamma = zeros (:563-567)
+            const int sid = j0 + (alive ? best : 0);
+            if (cplx[sid] <= lambda_c) break;                   // :572-573, before accumulating
+            const float gam = alive ? 1.0f / s : 0.f;           // gamma of the arg-max child
+            if (gam >= 1e-15f) {                                // accumulate() guard (:457-459)
+                if (sid < kTopNodes) {
+                    float* A = &s_top[sid][0];
+                    atomicAdd(A + 0, gam);
+                    atomicAdd(A + 1, gam * x);
+                    atomicAdd(A + 2, gam * y);
+                    atomicAdd(A + 3, gam * z);
+                    if (want_m2) {
+                        atomicAdd(A + 4, gam * x * x);
+                        atomicAdd(A + 5, gam * x * y);
+                        atomicAdd(A + 6, gam * x * z);
+                        atomicAdd(A + 7, gam * y * y);
+                        atomicAdd(A + 8, gam * y * z);
+                        atomicAdd(A + 9, gam * z * z);
+                    }
+                } else {
+                    double* A = racc + (size_t)sid * kRegMom;
+                    const double g = gam, X = x, Y = y, Z = z;
+                    atomicAdd(A + 0, g);
+                    atomicAdd(A + 1, g * X);
+                    atomicAdd(A + 2, g * Y);
+                    atomicAdd(A + 3, g * Z);
+                    if (want_m2) {
+                        atomicAdd(A + 4, g * X * X);
+                        atomicAdd(A + 5, g * X * Y);
+                        atomicAdd(A + 6, g * X * Z);
+                        atomicAdd(A + 7, g * Y * Y);
+                        atomicAdd(A + 8, g * Y * Z);
+                        atomicAdd(A + 9, g * Z * Z);
+                    }
+                }
+            }
+            j0 = (sid + 1) * 8;
         }
-        j0 = (sid + 1) * 8;
+    }
+    __syncthreads();
+    const int nm = want_m2 ? kRegMom : 4;
+    for (int k = threadIdx.x; k < kTopNodes * kRegMom; k += blockDim.x) {
+        const int node = k / kRegMom, mom = k - node * kRegMom;
+        const float v = s_top[node][mom];
+        if (mom < nm && v != 0.f) atomicAdd(racc + (size_t)node * kRegMom + mom, (double)v);
     }
 }
 

@@ -90,14 +90,17 @@ __global__ void __launch_bounds__(256) tree_estep_kernel(const float* __restrict
                                                          const int* __restrict__ n_chunks_dev,
                                                          const PackedComp* __restrict__ packed_level,
                                                          double* __restrict__ acc, uint8_t* __restrict__ slot,
-                                                         const int* __restrict__ ctrl) {
-    if (ctrl[0]) return;
+                                                         const int* __restrict__ done_flag) {
+    if (*done_flag) return;
     __shared__ __align__(16) float sch[8][96];
+    __shared__ float s_part[8][8 * kMom];     // per-warp chunk sums (80 floats)
+    __shared__ int s_parent[8];
     __shared__ double s_ll[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunk = blockIdx.x * 8 + warp;
     const int n_chunks = *n_chunks_dev;
     double ll = 0.0;
+    int my_parent = -1;                       // -1: this warp has no chunk
     if (chunk < n_chunks) {
         const int p = chunk_parent[chunk];
         const int start = chunk_start[chunk];
@@ -165,18 +168,193 @@ __global__ void __launch_bounds__(256) tree_estep_kernel(const float* __restrict
         reduce_scatter_step<10>(v, 2, (lane & 2) != 0);
 #pragma unroll
         for (int i = 0; i < 5; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+        my_parent = p;
         if ((lane & 1) == 0) {
             const int idx0 = ((lane & 16) ? 40 : 0) + ((lane & 8) ? 20 : 0) + ((lane & 4) ? 10 : 0) + ((lane & 2) ? 5 : 0);
-            double* dst = acc + kAccHdr + (size_t)p * (8 * kMom) + idx0;
 #pragma unroll
-            for (int i = 0; i < 5; ++i)
-                if (v[i] != 0.f) atomicAdd(dst + i, (double)v[i]);
+            for (int i = 0; i < 5; ++i) s_part[warp][idx0 + i] = v[i];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
     }
-    if (lane == 0) s_ll[warp] = ll;
+    if (lane == 0) {
+        s_ll[warp] = ll;
+        s_parent[warp] = my_parent;
+    }
     __syncthreads();
+    // Fold the CTA's 8 chunk sums: runs of consecutive warps with the same parent are added in fp32 (<= 8 terms) and
+    // leave as ONE set of <= 80 fp64 atomics -- at the top levels (few parents, thousands of chunks) this cuts the
+    // same-address atomic traffic 8x.  Thread t < 80 owns moment slot t.
+    if (tid < 8 * kMom) {
+        int run_parent = -1;
+        float run = 0.f;
+        for (int w = 0; w < 8; ++w) {
+            const int pw = s_parent[w];
+            if (pw != run_parent) {
+                if (run_parent >= 0 && run != 0.f) atomicAdd(acc + kAccHdr + (size_t)run_parent * (8 * kMom) + tid, (double)run);
+                run_parent = pw;
+                run = 0.f;
+            }
+            if (pw >= 0) run += s_part[w][tid];
+        }
+        if (run_parent >= 0 && run != 0.f) atomicAdd(acc + kAccHdr + (size_t)run_parent * (8 * kMom) + tid, (double)run);
+    }
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_ll[w];
+        if (t != 0.0) atomicAdd(acc, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// E-step, packed-FP32 version (default): one warp per chunk, lane = (child pair cp = lane/8, point lane pl = lane%8).
+// Each lane keeps ONE pair of children (FFMA2/FADD2/FMUL2 operands, 10 float2 moment accumulators, ~70 registers
+// instead of ~210), the 8-way normalisation is two xor-shuffles (8, 16) across the four lanes that share a point,
+// the fold over the eight point lanes is three xor-shuffles (1, 2, 4).  Same semantics as tree_estep_kernel.
+// ------------------------------------------------------------------------------------------
+typedef unsigned long long u64t;
+__device__ __forceinline__ float2 t_ffma2(float2 a, float2 b, float2 c) {
+    u64t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<u64t*>(&a)), "l"(*reinterpret_cast<u64t*>(&b)),
+        "l"(*reinterpret_cast<u64t*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 t_fadd2(float2 a, float2 b) {
+    u64t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64t*>(&a)), "l"(*reinterpret_cast<u64t*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 t_fmul2(float2 a, float2 b) {
+    u64t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64t*>(&a)), "l"(*reinterpret_cast<u64t*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
+__global__ void __launch_bounds__(256, 3) tree_estep2_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                             const float* __restrict__ pz,
+                                                             const int* __restrict__ chunk_parent,
+                                                             const int* __restrict__ chunk_start,
+                                                             const int* __restrict__ chunk_len,
+                                                             const int* __restrict__ n_chunks_dev,
+                                                             const PackedComp* __restrict__ packed_level,
+                                                             double* __restrict__ acc, uint8_t* __restrict__ slot,
+                                                             const int* __restrict__ done_flag) {
+    if (*done_flag) return;
+    __shared__ float s_part[8][8 * kMom];
+    __shared__ int s_parent[8];
+    __shared__ double s_ll[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cp = lane >> 3, pl = lane & 7;
+    const int chunk = blockIdx.x * 8 + warp;
+    const int n_chunks = *n_chunks_dev;
+    double ll = 0.0;
+    int my_parent = -1;
+    if (chunk < n_chunks) {
+        const int p = chunk_parent[chunk];
+        const int start = chunk_start[chunk];
+        const int len = chunk_len[chunk];
+        // the lane's pair of children (2cp, 2cp+1) of parent p
+        float2 nmx, nmy, nmz, c2, axx, ayy, azz, axy, axz, ayz;
+        {
+            const float4* a4 = reinterpret_cast<const float4*>(packed_level + 8 * (size_t)p + 2 * cp);
+            const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), a2 = __ldg(a4 + 2);
+            const float4 b0 = __ldg(a4 + 3), b1 = __ldg(a4 + 4), b2 = __ldg(a4 + 5);
+            nmx = make_float2(-a0.x, -b0.x); nmy = make_float2(-a0.y, -b0.y); nmz = make_float2(-a0.z, -b0.z);
+            c2 = make_float2(a0.w, b0.w);
+            axx = make_float2(a1.x, b1.x); ayy = make_float2(a1.y, b1.y); azz = make_float2(a1.z, b1.z);
+            axy = make_float2(a1.w, b1.w); axz = make_float2(a2.x, b2.x); ayz = make_float2(a2.y, b2.y);
+        }
+        float2 a[kMom];
+#pragma unroll
+        for (int m = 0; m < kMom; ++m) a[m] = make_float2(0.f, 0.f);
+
+        for (int rb = 0; rb < len; rb += 8) {                 // warp-uniform trip count: the shuffles need every lane
+            const int r = rb + pl;
+            const bool valid = r < len;
+            const int i = start + (valid ? r : len - 1);
+            const float x = px[i], y = py[i], z = pz[i];
+            const float2 dx = t_fadd2(make_float2(x, x), nmx), dy = t_fadd2(make_float2(y, y), nmy), dz = t_fadd2(make_float2(z, z), nmz);
+            float2 t0 = t_fmul2(axz, dz);
+            t0 = t_ffma2(axy, dy, t0);
+            t0 = t_ffma2(axx, dx, t0);
+            float2 t1 = t_fmul2(ayz, dz);
+            t1 = t_ffma2(ayy, dy, t1);
+            const float2 t2 = t_fmul2(azz, dz);
+            float2 q = t_ffma2(dz, t2, c2);
+            q = t_ffma2(dy, t1, q);
+            q = t_ffma2(dx, t0, q);
+            float m = fmaxf(fmaxf(q.x, q.y), kNegBig);
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+            const float2 e = make_float2(ex2f(q.x - m), ex2f(q.y - m));
+            float s = e.x + e.y;
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            int best = (q.x == m) ? 2 * cp : ((q.y == m) ? 2 * cp + 1 : 99);      // first maximum, like np.argmax
+            best = min(best, __shfl_xor_sync(0xffffffffu, best, 8));
+            best = min(best, __shfl_xor_sync(0xffffffffu, best, 16));
+            const float lse2 = m + lg2f(s);
+            // hgmm_cupy_cpu_working.py:174-178: gamma = gamma/den if den > eps else zeros
+            const bool alive = valid && (lse2 > kLog2Eps15);
+            if (valid && cp == 0) {
+                slot[i] = (uint8_t)((alive && best < 8) ? best : 0);
+                ll += (double)(kLn2 * fmaxf(alive ? lse2 : kLog2Eps15, kLog2Eps15));
+            }
+            const float inv = alive ? __fdividef(1.0f, s) : 0.f;
+            float2 gam = make_float2(e.x * inv, e.y * inv);
+            gam.x = (gam.x < 1e-15f) ? 0.f : gam.x;            // accumulate() skips gamma < eps (:100-101)
+            gam.y = (gam.y < 1e-15f) ? 0.f : gam.y;
+            const float2 gx = t_fmul2(gam, dx), gy = t_fmul2(gam, dy), gz = t_fmul2(gam, dz);
+            a[0] = t_fadd2(a[0], gam);
+            a[1] = t_fadd2(a[1], gx);
+            a[2] = t_fadd2(a[2], gy);
+            a[3] = t_fadd2(a[3], gz);
+            a[4] = t_ffma2(gx, dx, a[4]);
+            a[5] = t_ffma2(gx, dy, a[5]);
+            a[6] = t_ffma2(gx, dz, a[6]);
+            a[7] = t_ffma2(gy, dy, a[7]);
+            a[8] = t_ffma2(gy, dz, a[8]);
+            a[9] = t_ffma2(gz, dz, a[9]);
+        }
+        // fold the eight point lanes
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+#pragma unroll
+            for (int m = 0; m < kMom; ++m) {
+                a[m].x += __shfl_xor_sync(0xffffffffu, a[m].x, off);
+                a[m].y += __shfl_xor_sync(0xffffffffu, a[m].y, off);
+            }
+        }
+        my_parent = p;
+        if (pl == 0) {
+#pragma unroll
+            for (int m = 0; m < kMom; ++m) {
+                s_part[warp][(2 * cp) * kMom + m] = a[m].x;
+                s_part[warp][(2 * cp + 1) * kMom + m] = a[m].y;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+    }
+    if (lane == 0) {
+        s_ll[warp] = ll;
+        s_parent[warp] = my_parent;
+    }
+    __syncthreads();
+    if (tid < 8 * kMom) {                                   // same CTA-level fold as tree_estep_kernel
+        int run_parent = -1;
+        float run = 0.f;
+        for (int w = 0; w < 8; ++w) {
+            const int pw = s_parent[w];
+            if (pw != run_parent) {
+                if (run_parent >= 0 && run != 0.f) atomicAdd(acc + kAccHdr + (size_t)run_parent * (8 * kMom) + tid, (double)run);
+                run_parent = pw;
+                run = 0.f;
+            }
+            if (pw >= 0) run += s_part[w][tid];
+        }
+        if (run_parent >= 0 && run != 0.f) atomicAdd(acc + kAccHdr + (size_t)run_parent * (8 * kMom) + tid, (double)run);
+    }
     if (tid == 0) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += s_ll[w];
@@ -187,9 +365,28 @@ __global__ void __launch_bounds__(256) tree_estep_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------
 // M-step: one thread per node of the level
 // ------------------------------------------------------------------------------------------
+// done_at[it] is written by iteration it-1 only.  merge_converge != 0 (fast log-likelihood mode): thread 0 of block 0
+// also applies the |q - prevQ| < ls rule to acc[0] (complete: the E-step has finished) and arms done_at[it+1].
 __global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __restrict__ acc, double n_total, float ld,
-                                  const int* __restrict__ ctrl) {
-    if (ctrl[0]) return;
+                                  int* __restrict__ ctrl, int* __restrict__ done_at, int it, int merge_converge,
+                                  double* __restrict__ qstate, float ls, int max_iters) {
+    const bool done = done_at[it] != 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (done) {
+            done_at[it + 1] = 1;
+        } else if (merge_converge) {
+            const double q = acc[0];
+            acc[0] = 0.0;
+            const int n_it = ctrl[1] + 1;
+            ctrl[1] = n_it;
+            qstate[1] = q;
+            const bool conv = fabs(q - qstate[0]) < (double)ls || n_it >= max_iters;
+            qstate[0] = q;
+            ctrl[0] = conv ? 1 : 0;
+            done_at[it + 1] = conv ? 1 : 0;
+        }
+    }
+    if (done) return;
     const int local = blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= count) return;
     const int j = lb + local;
@@ -209,7 +406,6 @@ __global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __rest
         float* c = t.cov + 9 * j;
         c[0] = (float)s.xx; c[1] = c[3] = (float)s.xy; c[2] = c[6] = (float)s.xz;
         c[4] = (float)s.yy; c[5] = c[7] = (float)s.yz; c[8] = (float)s.zz;
-        t.cplx[j] = (float)sym3_complexity(s);
         t.packed[j] = pack_full(log(w), fx, fy, fz, s, false, 1e-15);
     } else {
         t.pi[j] = 0.f;
@@ -217,7 +413,6 @@ __global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __rest
         float* c = t.cov + 9 * j;
         c[0] = c[4] = c[8] = 1.f;
         c[1] = c[2] = c[3] = c[5] = c[6] = c[7] = 0.f;
-        t.cplx[j] = (float)(1.0 / 3.0);
         t.packed[j] = pack_full(-INFINITY, 0, 0, 0, Sym3{1, 0, 0, 1, 0, 1}, false, 1e-15);
     }
 #pragma unroll
@@ -225,21 +420,35 @@ __global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __rest
 }
 
 // |q - prevQ| < ls with prevQ = 0 at level start (hgmm_gpu.py:520,533-535).  qstate: [0] prevQ, [1] last q.
-__global__ void tree_converge_kernel(double* __restrict__ acc, int* __restrict__ ctrl, double* __restrict__ qstate, float ls,
-                                     int max_iters) {
-    if (ctrl[0]) return;
+__global__ void tree_converge_kernel(double* __restrict__ acc, int* __restrict__ ctrl, int* __restrict__ done_at, int it,
+                                     double* __restrict__ qstate, float ls, int max_iters) {
+    if (done_at[it]) {
+        done_at[it + 1] = 1;
+        return;
+    }
     const double q = acc[0];
     acc[0] = 0.0;
-    const int it = ctrl[1] + 1;
-    ctrl[1] = it;
+    const int n_it = ctrl[1] + 1;
+    ctrl[1] = n_it;
     qstate[1] = q;
-    if (fabs(q - qstate[0]) < (double)ls || it >= max_iters) ctrl[0] = 1;
+    const bool conv = fabs(q - qstate[0]) < (double)ls || n_it >= max_iters;
     qstate[0] = q;
+    ctrl[0] = conv ? 1 : 0;
+    done_at[it + 1] = conv ? 1 : 0;
 }
 
-__global__ void tree_zero_ll_kernel(double* __restrict__ acc, const int* __restrict__ ctrl) {
-    if (ctrl[0]) return;
+__global__ void tree_zero_ll_kernel(double* __restrict__ acc, const int* __restrict__ done_flag) {
+    if (*done_flag) return;
     acc[0] = 0.0;
+}
+
+// complexity of every node (registration pruning); run once after the build instead of inside every M-step
+__global__ void tree_cplx_kernel(TreeModel t) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= t.nt) return;
+    const float* c = t.cov + 9 * j;
+    Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
+    t.cplx[j] = (float)sym3_complexity(s);
 }
 
 // current[perm[i]] = level base + 8 * parent + slot  (hgmm_gpu.py:411)
@@ -453,23 +662,31 @@ void launch_tree_pack_all(const TreeModel& t, cudaStream_t s) {
 }
 
 cudaError_t launch_tree_estep(const TreeWork& w, const TreeModel& t, int level, double* acc, int n_chunks_bound,
-                              const int* n_chunks_dev, const int* ctrl, cudaStream_t s) {
+                              const int* n_chunks_dev, const int* done_flag, int scalar_variant, cudaStream_t s) {
     if (n_chunks_bound <= 0) return cudaSuccess;
     const int grid = (n_chunks_bound + 7) / 8;
+    if (!scalar_variant) {
+        tree_estep2_kernel<<<grid, 256, 0, s>>>(w.x, w.y, w.z, w.chunk_parent, w.chunk_start, w.chunk_len, n_chunks_dev,
+                                                t.packed + level_base(level), acc, w.slot, done_flag);
+        return cudaGetLastError();
+    }
     tree_estep_kernel<<<grid, 256, 0, s>>>(w.x, w.y, w.z, w.chunk_parent, w.chunk_start, w.chunk_len, n_chunks_dev,
-                                           t.packed + level_base(level), acc, w.slot, ctrl);
+                                           t.packed + level_base(level), acc, w.slot, done_flag);
     return cudaGetLastError();
 }
 
-void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_total, float ld, const int* ctrl, cudaStream_t s) {
+void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_total, float ld, int* ctrl, int* done_at, int it,
+                       int merge_converge, double* qstate, float ls, int max_iters, cudaStream_t s) {
     const int cnt = level_count(level);
-    tree_mstep_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(t, level_base(level), cnt, acc, n_total, ld, ctrl);
+    tree_mstep_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(t, level_base(level), cnt, acc, n_total, ld, ctrl, done_at, it, merge_converge,
+                                                        qstate, ls, max_iters);
 }
 
-void launch_tree_converge(double* acc, int* ctrl, double* qstate, float ls, int max_iters, cudaStream_t s) {
-    tree_converge_kernel<<<1, 1, 0, s>>>(acc, ctrl, qstate, ls, max_iters);
+void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, cudaStream_t s) {
+    tree_converge_kernel<<<1, 1, 0, s>>>(acc, ctrl, done_at, it, qstate, ls, max_iters);
 }
-void launch_tree_zero_ll(double* acc, const int* ctrl, cudaStream_t s) { tree_zero_ll_kernel<<<1, 1, 0, s>>>(acc, ctrl); }
+void launch_tree_zero_ll(double* acc, const int* done_flag, cudaStream_t s) { tree_zero_ll_kernel<<<1, 1, 0, s>>>(acc, done_flag); }
+void launch_tree_cplx(const TreeModel& t, cudaStream_t s) { tree_cplx_kernel<<<(t.nt + 127) / 128, 128, 0, s>>>(t); }
 
 void launch_tree_current(const TreeWork& w, int n, int level, int64_t* current, cudaStream_t s) {
     if (n <= 0) return;

@@ -131,11 +131,11 @@ class Engine:
         return int(L.load().hgmm_tree_total_nodes(int(max_level)))
 
     def fit_tree(self, init_means, max_level, ls=20.0, ld=1.0e-4, sig2=0.004, ll_mode="level", max_iters_per_level=10000,
-                 chunk_points=0, want_current=True, want_outputs=True):
+                 chunk_points=0, want_current=True, want_outputs=True, variant=0):
         nt = self.tree_total_nodes(max_level)
         init_means = L.f32c(init_means, (nt, 3))
         cfg = L.TreeConfig(int(max_level), L.LL_LEVEL if ll_mode == "level" else L.LL_ESTEP, float(ls), float(ld), float(sig2),
-                           int(max_iters_per_level), int(chunk_points), 0)
+                           int(max_iters_per_level), int(chunk_points), int(variant))
         pi = np.empty(nt, np.float32) if want_outputs else None
         mu = np.empty((nt, 3), np.float32) if want_outputs else None
         cov = np.empty((nt, 3, 3), np.float32) if want_outputs else None

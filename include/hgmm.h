@@ -83,7 +83,7 @@ typedef struct hgmm_tree_config {
     float sig2;                    /* initial isotropic variance (reference 0.004 GPU / 0.00034 CPU) */
     int32_t max_iters_per_level;   /* safety cap; the reference has none */
     int32_t chunk_points;          /* 0 = auto; points per warp work item (multiple of 32) */
-    int32_t reserved;
+    int32_t reserved;              /* E-step kernel: 0 = packed-FP32 (default), 1 = scalar first-generation kernel */
 } hgmm_tree_config;
 
 typedef struct hgmm_reg_config {

@@ -15,6 +15,14 @@ if what == "flat":
     eng.set_points(torch.from_numpy(X).cuda())
     for _ in range(3):
         eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False)
+elif what == "reg":
+    from hgmm_b200 import hgmm as H
+    S = np.load(os.path.join(ROOT, "tests/golden/bun000_xyz.npy")); T = np.load(os.path.join(ROOT, "tests/golden/bun045_xyz.npy"))
+    init = S[H.reference_init_indices(3)]
+    eng.set_points(torch.from_numpy(S).cuda()); eng.reg_set_target(torch.from_numpy(T).cuda())
+    for _ in range(2):
+        eng.fit_tree(init, 3, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False, want_outputs=False)
+        eng.register_tree(solver="twist_lstsq", maxiter=20, tol=1e-4)
 else:
     from oracle import synth
     from hgmm_b200 import hgmm as H

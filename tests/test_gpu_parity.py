@@ -199,14 +199,15 @@ def test_tree_build_matches_reference_golden(engine, tag):
     assert (r["current"] == g["oracle_current"]).mean() > 0.995
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("ll_mode", ["level", "estep"])
 @pytest.mark.parametrize("L,n", [(2, 5000), (3, 20000)])
-def test_tree_build_matches_oracle(engine, L, n, ll_mode):
+def test_tree_build_matches_oracle(engine, L, n, ll_mode, variant):
     from oracle import hgmm_tree, synth
     X = synth.bunny_like(n, seed=7)
     init = X[hgmm_tree.reference_init_indices(L)]
     engine.set_points(X)
-    r = engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode=ll_mode)
+    r = engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode=ll_mode, variant=variant)
     opi, omu, ocov, ocur, oit, _ = hgmm_tree.build_gmm_tree(X, L, 20.0, 1e-4, init.astype(np.float64), sig2=np.float32(4e-4),
                                                           ll_mode=ll_mode, return_trace=True)
     assert list(r["iters"]) == list(oit)
