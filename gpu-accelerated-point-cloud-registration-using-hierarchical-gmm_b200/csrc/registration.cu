@@ -19,6 +19,10 @@ constexpr int kRegMom = 10;     // M0, M1(3), raw M2 (xx xy xz yy yz zz) -- fp64
 // ------------------------------------------------------------------------------------------
 constexpr int kTopNodes = 72;       // levels 0 and 1 (8 + 64 nodes): accumulated per CTA in shared memory
 
+__device__ __forceinline__ unsigned long long to_fixed(double v) {       // two's-complement 27.36 fixed point
+    return (unsigned long long)__double2ll_rn(v * 68719476736.0);
+}
+
 __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict__ tx, const float* __restrict__ ty,
                                                         const float* __restrict__ tz, int n, const double* __restrict__ Rt,
                                                         const PackedComp* __restrict__ packed, const float* __restrict__ cplx,
@@ -26,10 +30,12 @@ __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict_
                                                         const int* __restrict__ ctrl) {
     if (ctrl[0]) return;
     // Every point visits level 0 and most visit level 1, i.e. 40k points land on 8 + 64 addresses: those two levels
-    // are summed per CTA with native fp32 shared-memory atomics (<= 256 terms) and flushed as one fp64 atomic per
+    // are summed per CTA with 64-bit integer shared-memory atomics (<= 256 terms) and flushed as one fp64 atomic per
     // touched slot; deeper levels (>= 512 nodes) go straight to fp64 global atomics.
-    __shared__ float s_top[kTopNodes][kRegMom];
-    for (int k = threadIdx.x; k < kTopNodes * kRegMom; k += blockDim.x) (&s_top[0][0])[k] = 0.f;
+    // (64-bit fixed point, 2^-36 resolution: exact, order-independent sums -- the q-based stopping rule of the
+    //  registration loop is sensitive to 1e-7 relative noise in these moments)
+    __shared__ unsigned long long s_top[kTopNodes][kRegMom];
+    for (int k = threadIdx.x; k < kTopNodes * kRegMom; k += blockDim.x) (&s_top[0][0])[k] = 0ull;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -64,18 +70,19 @@ __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict_
             const float gam = alive ? 1.0f / s : 0.f;           // gamma of the arg-max child
             if (gam >= 1e-15f) {                                // accumulate() guard (:457-459)
                 if (sid < kTopNodes) {
-                    float* A = &s_top[sid][0];
-                    atomicAdd(A + 0, gam);
-                    atomicAdd(A + 1, gam * x);
-                    atomicAdd(A + 2, gam * y);
-                    atomicAdd(A + 3, gam * z);
+                    unsigned long long* A = &s_top[sid][0];
+                    const double g = gam, X = x, Y = y, Z = z;
+                    atomicAdd(A + 0, to_fixed(g));
+                    atomicAdd(A + 1, to_fixed(g * X));
+                    atomicAdd(A + 2, to_fixed(g * Y));
+                    atomicAdd(A + 3, to_fixed(g * Z));
                     if (want_m2) {
-                        atomicAdd(A + 4, gam * x * x);
-                        atomicAdd(A + 5, gam * x * y);
-                        atomicAdd(A + 6, gam * x * z);
-                        atomicAdd(A + 7, gam * y * y);
-                        atomicAdd(A + 8, gam * y * z);
-                        atomicAdd(A + 9, gam * z * z);
+                        atomicAdd(A + 4, to_fixed(g * X * X));
+                        atomicAdd(A + 5, to_fixed(g * X * Y));
+                        atomicAdd(A + 6, to_fixed(g * X * Z));
+                        atomicAdd(A + 7, to_fixed(g * Y * Y));
+                        atomicAdd(A + 8, to_fixed(g * Y * Z));
+                        atomicAdd(A + 9, to_fixed(g * Z * Z));
                     }
                 } else {
                     double* A = racc + (size_t)sid * kRegMom;
@@ -101,8 +108,8 @@ __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict_
     const int nm = want_m2 ? kRegMom : 4;
     for (int k = threadIdx.x; k < kTopNodes * kRegMom; k += blockDim.x) {
         const int node = k / kRegMom, mom = k - node * kRegMom;
-        const float v = s_top[node][mom];
-        if (mom < nm && v != 0.f) atomicAdd(racc + (size_t)node * kRegMom + mom, (double)v);
+        const unsigned long long v = s_top[node][mom];
+        if (mom < nm && v != 0ull) atomicAdd(racc + (size_t)node * kRegMom + mom, (double)(long long)v * (1.0 / 68719476736.0));
     }
 }
 
