@@ -698,8 +698,8 @@ int hgmm_reg_mstep(hgmm_ctx* ctx, int32_t solver, double* rot, double* t, double
     CK(ctx->hist.ensure(8 * sizeof(double)));
     CK(cudaMemsetAsync(ctx->ctrl.p, 0, 8 * sizeof(int), s));
     CK(cudaMemsetAsync(ctx->qstate.p, 0, 4 * sizeof(double), s));
-    CK(launch_reg_solve(ctx->tm, ctx->racc.as<double>(), solver, ctx->Rt.as<double>(), ctx->hist.as<double>(), ctx->qstate.as<double>(),
-                        ctx->ctrl.as<int>(), 0.f, s));
+    CK(launch_reg_solve(ctx->tm, ctx->racc.as<double>(), 0, solver, ctx->Rt.as<double>(), ctx->hist.as<double>(),
+                        ctx->qstate.as<double>(), ctx->ctrl.as<int>(), 0.f, s));
     ctx->launches += 1;
     CK(cudaMemcpyAsync(ctx->h_dbl, ctx->Rt.p, 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_dbl + 16, ctx->qstate.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -731,20 +731,21 @@ int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, d
     int* ctrl = ctx->ctrl.as<int>();
     CK(cudaMemsetAsync(ctrl, 0, 8 * sizeof(int), s));
     CK(cudaMemsetAsync(ctx->qstate.p, 0, 4 * sizeof(double), s));
+    CK(cudaMemsetAsync(ctx->racc.p, 0, rn * sizeof(double), s));
     CK(cudaEventRecord(ctx->ev0, s));
     const int batch = 4;
     int issued = 0;
     bool done = false;
     while (!done && issued < cfg->maxiter) {
         for (int b = 0; b < batch && issued < cfg->maxiter; ++b, ++issued) {
-            launch_zero_doubles(ctx->racc.as<double>(), rn, ctrl, s);
+            // the solve kernel zeroes the moments it consumed, so no separate clearing launch is needed per iteration
             CK(launch_reg_estep(ctx->tx.as<float>(), ctx->ty.as<float>(), ctx->tz.as<float>(), ctx->nt_pts, ctx->Rt.as<double>(), tm,
                                 cfg->lambda_c, ctx->racc.as<double>(), 0, ctrl, s));
             r = allreduce(ctx, ctx->racc.as<double>(), rn);
             if (r != HGMM_OK) return r;
-            CK(launch_reg_solve(tm, ctx->racc.as<double>(), cfg->solver, ctx->Rt.as<double>(), ctx->hist.as<double>(),
+            CK(launch_reg_solve(tm, ctx->racc.as<double>(), 1, cfg->solver, ctx->Rt.as<double>(), ctx->hist.as<double>(),
                                 ctx->qstate.as<double>(), ctrl, cfg->tol, s));
-            ctx->launches += 3;
+            ctx->launches += 2;
         }
         CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -763,7 +764,7 @@ int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, d
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_ms[0] = ms; ctx->last_ms[1] = ms; ctx->last_ms[2] = 0;
-    ctx->have_racc = true;
+    ctx->have_racc = false;       // the loop's solve kernel consumed (zeroed) the moments
     if (ctx->h_ctrl[2]) FAIL(HGMM_ERR_NUMERIC, "registration solve: singular / non-positive-definite system");
     return HGMM_OK;
 }

@@ -373,39 +373,36 @@ __global__ void __launch_bounds__(128) flat_finalize_kernel(FlatModel m, const d
     block_max_c2(my_c2, m.cref_blocks, m.Jp >> 5);
 }
 
-// Single-GPU fusion of flat_reduce_kernel + flat_finalize_kernel: one CTA per 32-component slot, 32 warps.
-// warp w < 30: moment w % 10, row group w / 10 of 3; warp 30: sum of log-lik / live counts; then lanes of warp 0
-// finalize their component.  cref_blocks gets one entry per slot (n_cref = Jp / 32 in this mode).
-__global__ void __launch_bounds__(1024) flat_reduce_finalize_kernel(FlatModel m, const float* __restrict__ partial,
-                                                                    const double* __restrict__ rowaux, int rows,
-                                                                    int* __restrict__ ctrl, int* __restrict__ done_at, int it,
-                                                                    double* __restrict__ ll_hist, double n_total) {
+// Single-GPU fusion of flat_reduce_kernel + flat_finalize_kernel: one CTA per 32-component slot, 16 warps.
+// Warp w sums rows w, w+16, ... for all 10 moments of its lane's component (all loads independent -> one round trip),
+// the 16 warp partials are added in a fixed order by warp 0, whose lanes then finalize their component.
+__global__ void __launch_bounds__(512) flat_reduce_finalize_kernel(FlatModel m, const float* __restrict__ partial,
+                                                                   const double* __restrict__ rowaux, int rows,
+                                                                   int* __restrict__ ctrl, int* __restrict__ done_at, int it,
+                                                                   double* __restrict__ ll_hist, double n_total) {
     const bool done = done_at[it] != 0;
     if (done) {
         if (blockIdx.x == 0 && threadIdx.x == 0) done_at[it + 1] = 1;
         return;
     }
-    __shared__ double sm[3][kMom][33];
-    __shared__ double s_aux[2];
+    __shared__ double sm[16][kMom][33];
+    __shared__ double s_aux[16][2];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int j = blockIdx.x * 32 + lane;
-    if (w < 30) {
-        const int k = w % kMom, rg = w / kMom;
-        const float* src = partial + (size_t)k * m.Jp + j;
+    {
+        double v[kMom];
+#pragma unroll
+        for (int k = 0; k < kMom; ++k) v[k] = 0.0;
         const size_t stride = (size_t)kMom * m.Jp;
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        int r = rg;
-        for (; r + 9 < rows; r += 12) {
-            v0 += (double)src[(size_t)r * stride];
-            v1 += (double)src[(size_t)(r + 3) * stride];
-            v2 += (double)src[(size_t)(r + 6) * stride];
-            v3 += (double)src[(size_t)(r + 9) * stride];
+        for (int r = w; r < rows; r += 16) {
+            const float* src = partial + (size_t)r * stride + j;
+#pragma unroll
+            for (int k = 0; k < kMom; ++k) v[k] += (double)src[(size_t)k * m.Jp];
         }
-        for (; r < rows; r += 3) v0 += (double)src[(size_t)r * stride];
-        sm[rg][k][lane] = (v0 + v1) + (v2 + v3);
-    } else if (w == 30) {
-        double l = 0.0, c = 0.0;
-        for (int q = lane; q < rows; q += 32) {
+#pragma unroll
+        for (int k = 0; k < kMom; ++k) sm[w][k][lane] = v[k];
+        double l = 0.0, c = 0.0;                 // every warp also folds a slice of the per-row log-lik / live counts
+        for (int q = w * 32 + lane; q < rows; q += 512) {
             l += rowaux[2 * q];
             c += rowaux[2 * q + 1];
         }
@@ -415,21 +412,31 @@ __global__ void __launch_bounds__(1024) flat_reduce_finalize_kernel(FlatModel m,
             c += __shfl_xor_sync(0xffffffffu, c, o);
         }
         if (lane == 0) {
-            s_aux[0] = l;
-            s_aux[1] = c;
+            s_aux[w][0] = l;
+            s_aux[w][1] = c;
         }
     }
     __syncthreads();
     if (w == 0) {
         double A[kMom];
 #pragma unroll
-        for (int k = 0; k < kMom; ++k) A[k] = (sm[0][k][lane] + sm[1][k][lane]) + sm[2][k][lane];
+        for (int k = 0; k < kMom; ++k) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) t += sm[q][k][lane];
+            A[k] = t;
+        }
+        double ll = 0.0, total = 0.0;
+        for (int q = 0; q < 16; ++q) {
+            ll += s_aux[q][0];
+            total += s_aux[q][1];
+        }
         float my_c2 = -INFINITY;
-        if (j < m.J) my_c2 = finalize_component(m, j, A, s_aux[1], n_total);
+        if (j < m.J) my_c2 = finalize_component(m, j, A, total, n_total);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) my_c2 = fmaxf(my_c2, __shfl_xor_sync(0xffffffffu, my_c2, o));
         if (lane == 0) m.cref_blocks[blockIdx.x] = my_c2;
-        if (blockIdx.x == 0 && lane == 0) finalize_bookkeeping(m, s_aux[0], ctrl, done_at, it, ll_hist, n_total);
+        if (blockIdx.x == 0 && lane == 0) finalize_bookkeeping(m, ll, ctrl, done_at, it, ll_hist, n_total);
     }
 }
 
@@ -571,7 +578,7 @@ void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s) {
 }
 void launch_flat_reduce_finalize(const FlatModel& m, const float* partial, const double* rowaux, int rows, int* ctrl, int* done_at,
                                  int it, double* ll_hist, double n_total, cudaStream_t s) {
-    flat_reduce_finalize_kernel<<<m.Jp / 32, 1024, 0, s>>>(m, partial, rowaux, rows, ctrl, done_at, it, ll_hist, n_total);
+    flat_reduce_finalize_kernel<<<m.Jp / 32, 512, 0, s>>>(m, partial, rowaux, rows, ctrl, done_at, it, ll_hist, n_total);
 }
 
 void launch_flat_finalize(const FlatModel& m, const double* acc, int* ctrl, int* done_at, int it, double* ll_hist, double n_total,

@@ -107,8 +107,8 @@ cudaError_t launch_root_chunks(TreeWork& w, int n, const PartitionScratch& ps, i
 // registration.cu
 cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, int n, const double* Rt, const TreeModel& t,
                              float lambda_c, double* racc, int want_m2, const int* ctrl, cudaStream_t s);
-cudaError_t launch_reg_solve(const TreeModel& t, const double* racc, int solver, double* Rt, double* q_hist, double* qstate,
-                             int* ctrl, float tol, cudaStream_t s);
+cudaError_t launch_reg_solve(const TreeModel& t, double* racc, int zero_after, int solver, double* Rt, double* q_hist,
+                             double* qstate, int* ctrl, float tol, cudaStream_t s);
 void launch_zero_doubles(double* p, size_t n, const int* ctrl, cudaStream_t s);
 void launch_fill_vbo(const float* x, const float* y, const float* z, int64_t n, int64_t offset, float* vbo_pos, float* vbo_col,
                      float scene_scale, float r, float g, float b, cudaStream_t s);

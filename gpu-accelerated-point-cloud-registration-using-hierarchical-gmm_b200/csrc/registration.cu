@@ -17,27 +17,27 @@ constexpr int kRegMom = 10;     // M0, M1(3), raw M2 (xx xy xz yy yz zz) -- fp64
 // ------------------------------------------------------------------------------------------
 // E-step: one thread per target point, greedy root->leaf descent
 // ------------------------------------------------------------------------------------------
-constexpr int kTopNodes = 72;       // levels 0 and 1 (8 + 64 nodes): accumulated per CTA in shared memory
+constexpr int kTopNodes = 72;       // levels 0 and 1 (8 + 64 nodes) are folded per CTA without atomics
 
-__device__ __forceinline__ unsigned long long to_fixed(double v) {       // two's-complement 27.36 fixed point
-    return (unsigned long long)__double2ll_rn(v * 68719476736.0);
-}
-
+// E-step: one thread per target point, greedy root->leaf descent.
+// Every point visits level 0 and most visit level 1, i.e. 40k points would land on 8 + 64 addresses.  Those two
+// levels are therefore NOT accumulated with atomics: each thread parks (node, gamma) for its level-0 and level-1 visit
+// in shared memory, and after the descent warp w sums the parked entries of "its" nodes (node w of level 0, nodes
+// 8+8w..8+8w+7 of level 1) in fp64 in a fixed order, one fp64 global atomic per (node, moment, CTA).  Deeper levels
+// (>= 512 nodes) go straight to fp64 global atomics.
 __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict__ tx, const float* __restrict__ ty,
                                                         const float* __restrict__ tz, int n, const double* __restrict__ Rt,
                                                         const PackedComp* __restrict__ packed, const float* __restrict__ cplx,
                                                         int L, float lambda_c, double* __restrict__ racc, int want_m2,
                                                         const int* __restrict__ ctrl) {
     if (ctrl[0]) return;
-    // Every point visits level 0 and most visit level 1, i.e. 40k points land on 8 + 64 addresses: those two levels
-    // are summed per CTA with 64-bit integer shared-memory atomics (<= 256 terms) and flushed as one fp64 atomic per
-    // touched slot; deeper levels (>= 512 nodes) go straight to fp64 global atomics.
-    // (64-bit fixed point, 2^-36 resolution: exact, order-independent sums -- the q-based stopping rule of the
-    //  registration loop is sensitive to 1e-7 relative noise in these moments)
-    __shared__ unsigned long long s_top[kTopNodes][kRegMom];
-    for (int k = threadIdx.x; k < kTopNodes * kRegMom; k += blockDim.x) (&s_top[0][0])[k] = 0ull;
-    __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float s_x[256], s_y[256], s_z[256];
+    __shared__ float s_g[2][256];
+    __shared__ short s_node[2][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * blockDim.x + tid;
+    s_node[0][tid] = -1;
+    s_node[1][tid] = -1;
     if (i < n) {
         float x, y, z;
         {
@@ -46,6 +46,9 @@ __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict_
             y = (float)(Rt[3] * a + Rt[4] * b + Rt[5] * c + Rt[10]);
             z = (float)(Rt[6] * a + Rt[7] * b + Rt[8] * c + Rt[11]);
         }
+        s_x[tid] = x;
+        s_y[tid] = y;
+        s_z[tid] = z;
         int j0 = 0;                                             // child(-1) = 0
         for (int l = 0; l < L; ++l) {
             const float4* c4 = reinterpret_cast<const float4*>(packed + j0);
@@ -69,21 +72,9 @@ __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict_
             if (cplx[sid] <= lambda_c) break;                   // :572-573, before accumulating
             const float gam = alive ? 1.0f / s : 0.f;           // gamma of the arg-max child
             if (gam >= 1e-15f) {                                // accumulate() guard (:457-459)
-                if (sid < kTopNodes) {
-                    unsigned long long* A = &s_top[sid][0];
-                    const double g = gam, X = x, Y = y, Z = z;
-                    atomicAdd(A + 0, to_fixed(g));
-                    atomicAdd(A + 1, to_fixed(g * X));
-                    atomicAdd(A + 2, to_fixed(g * Y));
-                    atomicAdd(A + 3, to_fixed(g * Z));
-                    if (want_m2) {
-                        atomicAdd(A + 4, to_fixed(g * X * X));
-                        atomicAdd(A + 5, to_fixed(g * X * Y));
-                        atomicAdd(A + 6, to_fixed(g * X * Z));
-                        atomicAdd(A + 7, to_fixed(g * Y * Y));
-                        atomicAdd(A + 8, to_fixed(g * Y * Z));
-                        atomicAdd(A + 9, to_fixed(g * Z * Z));
-                    }
+                if (l < 2) {
+                    s_node[l][tid] = (short)sid;
+                    s_g[l][tid] = gam;
                 } else {
                     double* A = racc + (size_t)sid * kRegMom;
                     const double g = gam, X = x, Y = y, Z = z;
@@ -105,11 +96,33 @@ __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict_
         }
     }
     __syncthreads();
+    // ---- fold levels 0 and 1: warp w owns node w (level 0) and nodes 8 + 8w .. 8 + 8w + 7 (level 1)
     const int nm = want_m2 ? kRegMom : 4;
-    for (int k = threadIdx.x; k < kTopNodes * kRegMom; k += blockDim.x) {
-        const int node = k / kRegMom, mom = k - node * kRegMom;
-        const unsigned long long v = s_top[node][mom];
-        if (mom < nm && v != 0ull) atomicAdd(racc + (size_t)node * kRegMom + mom, (double)(long long)v * (1.0 / 68719476736.0));
+    for (int slot = 0; slot < 9; ++slot) {
+        const int lvl = slot == 0 ? 0 : 1;
+        const int node = slot == 0 ? warp : 8 + 8 * warp + (slot - 1);
+        double v[kRegMom];
+#pragma unroll
+        for (int k = 0; k < kRegMom; ++k) v[k] = 0.0;
+        for (int t = lane; t < 256; t += 32) {
+            if (s_node[lvl][t] == node) {
+                const double g = s_g[lvl][t], X = s_x[t], Y = s_y[t], Z = s_z[t];
+                v[0] += g; v[1] += g * X; v[2] += g * Y; v[3] += g * Z;
+                if (want_m2) {
+                    v[4] += g * X * X; v[5] += g * X * Y; v[6] += g * X * Z; v[7] += g * Y * Y; v[8] += g * Y * Z; v[9] += g * Z * Z;
+                }
+            }
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, v[0] != 0.0);
+        if (any == 0u) continue;                               // warp-uniform
+        for (int k = 0; k < nm; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        }
+        if (lane == 0) {
+            for (int k = 0; k < nm; ++k)
+                if (v[k] != 0.0) atomicAdd(racc + (size_t)node * kRegMom + k, v[k]);
+        }
     }
 }
 
@@ -119,16 +132,25 @@ __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict_
 constexpr int kSys = 28;        // H (21 upper-triangular) + g (6) + c (1)
 constexpr int kPro = 18;        // W, sum w s (3), sum w mu (3), sum w s mu^T (9), sum w |s|^2, sum w |mu|^2
 
+// fixed-order block sum of NV doubles per thread: xor-shuffle inside each warp, then thread 0 adds the warp totals
 template <int NV>
-__device__ void block_reduce(double* v, double* sm /*[blockDim][NV]*/, int tid, int nthreads) {
-    for (int k = 0; k < NV; ++k) sm[(size_t)k * nthreads + tid] = v[k];
-    __syncthreads();
-    for (int o = nthreads >> 1; o > 0; o >>= 1) {
-        if (tid < o)
-            for (int k = 0; k < NV; ++k) sm[(size_t)k * nthreads + tid] += sm[(size_t)k * nthreads + tid + o];
-        __syncthreads();
+__device__ void block_reduce(double* v, double* sm /*[nwarps][NV]*/, int tid, int nthreads) {
+    const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     }
-    for (int k = 0; k < NV; ++k) v[k] = sm[(size_t)k * nthreads];
+    if (lane == 0)
+        for (int k = 0; k < NV; ++k) sm[warp * NV + k] = v[k];
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 0; k < NV; ++k) {
+            double t = 0.0;
+            for (int w = 0; w < nw; ++w) t += sm[w * NV + k];
+            v[k] = t;
+        }
+    }
 }
 
 __device__ void rodrigues(const double* w, double* R) {      // twist_trans (hgmm_gpu.py:646-664)
@@ -282,19 +304,20 @@ __device__ double det3(const double M[3][3]) {
 }
 
 // ctrl: [0] done, [1] iterations, [2] numeric failure flag.  qstate: [0] previous q, [1] last q, [2] has-previous flag
-__global__ void __launch_bounds__(128) reg_solve_kernel(TreeModel t, const double* __restrict__ racc, int solver,
+__global__ void __launch_bounds__(512) reg_solve_kernel(TreeModel t, double* __restrict__ racc, int zero_after, int solver,
                                                         double* __restrict__ Rt, double* __restrict__ q_hist,
                                                         double* __restrict__ qstate, int* __restrict__ ctrl, float tol) {
     if (ctrl[0]) return;
-    extern __shared__ double sm[];
+    __shared__ double sm[16 * kSys];
     const int tid = threadIdx.x, nth = blockDim.x;
     const double f32eps = 1.1920928955078125e-07;            // np.finfo(np.float32).eps  (hgmm_gpu.py:741)
     if (solver == HGMM_SOLVER_TWIST_LSTSQ) {
         double v[kSys];
         for (int k = 0; k < kSys; ++k) v[k] = 0.0;
         for (int i = tid; i < t.nt; i += nth) {
-            const double* A = racc + (size_t)i * kRegMom;
-            const double M0 = A[0];
+            double* A = racc + (size_t)i * kRegMom;
+            const double M0 = A[0], S1x = A[1], S1y = A[2], S1z = A[3];
+            if (zero_after) { A[0] = 0.0; A[1] = 0.0; A[2] = 0.0; A[3] = 0.0; }
             if (M0 < f32eps) continue;
             const float* c = t.cov + 9 * i;
             Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
@@ -303,7 +326,7 @@ __global__ void __launch_bounds__(128) reg_solve_kernel(TreeModel t, const doubl
             const Sym3 ad = sym3_adj(s);
             const double r = 1.0 / det;
             const double P[3][3] = {{ad.xx * r, ad.xy * r, ad.xz * r}, {ad.xy * r, ad.yy * r, ad.yz * r}, {ad.xz * r, ad.yz * r, ad.zz * r}};
-            const double sx = A[1] / M0, sy = A[2] / M0, sz = A[3] / M0;
+            const double sx = S1x / M0, sy = S1y / M0, sz = S1z / M0;
             const double rr[3] = {t.mu[3 * i] - sx, t.mu[3 * i + 1] - sy, t.mu[3 * i + 2] - sz};
             // J = [ -[s]x | I ]  (3x6);  rows of J^T are the 6 unknowns
             const double Jm[3][6] = {{0, sz, -sy, 1, 0, 0}, {-sz, 0, sx, 0, 1, 0}, {sy, -sx, 0, 0, 0, 1}};
@@ -349,10 +372,11 @@ __global__ void __launch_bounds__(128) reg_solve_kernel(TreeModel t, const doubl
         double v[kPro];
         for (int k = 0; k < kPro; ++k) v[k] = 0.0;
         for (int i = tid; i < t.nt; i += nth) {
-            const double* A = racc + (size_t)i * kRegMom;
-            const double w = A[0];
+            double* A = racc + (size_t)i * kRegMom;
+            const double w = A[0], S1x = A[1], S1y = A[2], S1z = A[3];
+            if (zero_after) { A[0] = 0.0; A[1] = 0.0; A[2] = 0.0; A[3] = 0.0; }
             if (w < f32eps) continue;
-            const double s[3] = {A[1] / w, A[2] / w, A[3] / w};
+            const double s[3] = {S1x / w, S1y / w, S1z / w};
             const double m[3] = {t.mu[3 * i], t.mu[3 * i + 1], t.mu[3 * i + 2]};
             v[0] += w;
             for (int a = 0; a < 3; ++a) {
@@ -436,11 +460,9 @@ cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_reg_solve(const TreeModel& t, const double* racc, int solver, double* Rt, double* q_hist, double* qstate,
-                             int* ctrl, float tol, cudaStream_t s) {
-    const int nth = 128;                                    // 28 x 128 doubles = 28 KB of dynamic shared memory
-    const size_t smem = (size_t)kSys * nth * sizeof(double);
-    reg_solve_kernel<<<1, nth, smem, s>>>(t, racc, solver, Rt, q_hist, qstate, ctrl, tol);
+cudaError_t launch_reg_solve(const TreeModel& t, double* racc, int zero_after, int solver, double* Rt, double* q_hist,
+                             double* qstate, int* ctrl, float tol, cudaStream_t s) {
+    reg_solve_kernel<<<1, 512, 0, s>>>(t, racc, zero_after, solver, Rt, q_hist, qstate, ctrl, tol);
     return cudaGetLastError();
 }
 
