@@ -373,6 +373,262 @@ __global__ void __launch_bounds__(MAXT, MINB) em_flat3_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// em_flat4_kernel: em_flat3_kernel<.., PB=8, NP=1> with the batch loop software-pipelined.
+// The group barrier of batch k+1 is split into an mbarrier ARRIVE (right after pass 1 of batch k+1 published its
+// partial sums) and a WAIT placed after pass 2 of batch k, so the barrier latency and the finishing step hide behind
+// FFMA2 work and the warps of a CTA drift apart instead of marching through FMA-heavy and idle phases together.
+// e = 2^(q - Cref) is double-buffered in registers (two batches in flight), the partial-sum buffers are 4-deep
+// (a fast warp may publish batch k+2 while a slow one still folds batch k-1), two mbarriers alternate by batch parity.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) em_flat4_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                           const float* __restrict__ pz, int n,
+                                                           const PackedComp* __restrict__ packed,
+                                                           const float* __restrict__ cref_blocks, int n_cref, int J, int Jp,
+                                                           int Sdiv, int G, float* __restrict__ partial,
+                                                           double* __restrict__ rowaux, const int* __restrict__ done_flag,
+                                                           float norm_eps_on) {
+    if (*done_flag) return;
+    constexpr int PB = 8;
+    __shared__ __align__(16) float4 spts[kChunk3][2];            // (x,x,y,y) (z,z,0,0)
+    __shared__ __align__(16) float red[4][8][PB][16];            // [batch & 3][group][point][warp of group]
+    __shared__ __align__(16) float redslow[8][PB][16];           // rare path scratch
+    __shared__ __align__(16) float2 fin[16][PB];                 // [warp][point] (inv, inv), private to each warp
+    __shared__ __align__(16) float finmax[8][PB];
+    __shared__ uint64_t bars[8][2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 4 * 8 * PB * 16; i += blockDim.x) (&red[0][0][0][0])[i] = 0.f;
+    for (int i = tid; i < 8 * PB * 16; i += blockDim.x) (&redslow[0][0][0])[i] = 0.f;
+    const int g = warp / Sdiv, sw = warp - g * Sdiv;
+    const int gthreads = Sdiv * 32;
+    const int S = Jp >> 5;
+    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const bool rwriter = (lane & 3) == 0;
+    if (tid < 16) mbar_init(&bars[tid >> 1][tid & 1], Sdiv);
+    if (tid == 0) mbar_fence_init();
+
+    float cref = -INFINITY;
+    for (int i = 0; i < n_cref; ++i) cref = fmaxf(cref, __ldg(cref_blocks + i));
+    if (!(cref > kNegBig)) cref = 0.f;
+
+    PairParams k;
+    bool live0, live1;
+    {
+        const int s0 = sw, s1 = sw + Sdiv;
+        live0 = s0 < S;
+        live1 = s1 < S;
+        const float4* a4 = reinterpret_cast<const float4*>(packed + (live0 ? s0 * 32 + lane : 0));
+        const float4* b4 = reinterpret_cast<const float4*>(packed + (live1 ? s1 * 32 + lane : 0));
+        const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), a2 = __ldg(a4 + 2);
+        const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1), b2 = __ldg(b4 + 2);
+        k.nmx = make_float2(-a0.x, -b0.x);
+        k.nmy = make_float2(-a0.y, -b0.y);
+        k.nmz = make_float2(-a0.z, -b0.z);
+        k.c2 = make_float2(live0 ? a0.w - cref : -INFINITY, live1 ? b0.w - cref : -INFINITY);
+        k.axx = make_float2(a1.x, b1.x);
+        k.ayy = make_float2(a1.y, b1.y);
+        k.azz = make_float2(a1.z, b1.z);
+        k.axy = make_float2(a1.w, b1.w);
+        k.axz = make_float2(a2.x, b2.x);
+        k.ayz = make_float2(a2.y, b2.y);
+    }
+    float2 a[kMom];
+#pragma unroll
+    for (int m = 0; m < kMom; ++m) a[m] = make_float2(0.f, 0.f);
+    double ll = 0.0, nlive = 0.0;
+
+    const int per = (int)(((long long)n + gridDim.x - 1) / gridDim.x);
+    const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
+    unsigned kb = 0;                                     // running batch counter of this group (selects buffers / parities)
+
+    // pass 1 of the batch starting at `b`: e -> E[], partial sums -> red[kk & 3], arrive on bars[g][kk & 1]
+#define HGMM_PASS1(E, b, kk)                                                                                           \
+    {                                                                                                                  \
+        float sm_[PB];                                                                                                 \
+        _Pragma("unroll") for (int p = 0; p < PB; ++p) {                                                             \
+            const int ip = min((b) + p, cn - 1);                                                                       \
+            const float4 P0 = spts[ip][0], P1 = spts[ip][1];                                                          \
+            float2 dx, dy, dz;                                                                                         \
+            const float2 q = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz); \
+            E[p] = make_float2(ex2f(q.x), ex2f(q.y));                                                                  \
+            sm_[p] = E[p].x + E[p].y;                                                                                  \
+        }                                                                                                              \
+        reduce_scatter<PB>(sm_, lane, false);                                                                          \
+        if (rwriter) red[(kk) & 3][g][ridx][sw] = sm_[0];                                                              \
+        __syncwarp();                                                                                                  \
+        if (lane == 0) mbar_arrive(&bars[g][(kk) & 1]);                                                                \
+    }
+
+    for (int cb = lo; cb < hi; cb += kChunk3) {
+        const int cn = min(kChunk3, hi - cb);
+        __syncthreads();                                   // previous chunk fully consumed (also orders the inits above)
+        for (int i = tid; i < cn; i += blockDim.x) {
+            const float x = px[cb + i], y = py[cb + i], z = pz[cb + i];
+            spts[i][0] = make_float4(x, x, y, y);
+            spts[i][1] = make_float4(z, z, 0.f, 0.f);
+        }
+        __syncthreads();
+        const int gper = (cn + G - 1) / G;
+        const int gs = min(cn, g * gper), ge = min(cn, gs + gper);
+        if (gs >= ge) continue;
+        float2 e[2][PB];
+        HGMM_PASS1(e[0], gs, kb)
+        for (int b = gs; b < ge; b += 2 * PB) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {                  // u is a compile-time constant after unrolling: e[u] stays in registers
+                const int bc = b + u * PB;                 // current batch
+                if (bc < ge) {
+                    const int bn = bc + PB;                // next batch
+                    if (bn < ge) HGMM_PASS1(e[u ^ 1], bn, kb + 1)
+                    mbar_wait(&bars[g][kb & 1], (kb >> 1) & 1);
+                    const int np = min(PB, ge - bc);
+                    // ---------------- finishing (every warp, lanes 0..7)
+                    bool under = false;
+                    if (lane < PB) {
+                        const float4* r4 = reinterpret_cast<const float4*>(&red[kb & 3][g][lane][0]);
+                        const float4 r0 = r4[0], r1 = r4[1], r2 = r4[2], r3 = r4[3];
+                        const float v = (((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w))) +
+                                        (((r2.x + r2.y) + (r2.z + r2.w)) + ((r3.x + r3.y) + (r3.z + r3.w)));
+                        const bool valid = lane < np;
+                        under = valid && !(v >= kUnder3);
+                        float inv = (valid && !under) ? __fdividef(1.0f, v) : 0.f;
+                        if (norm_eps_on != 0.f || sw == 0) {
+                            if (valid && !under) {
+                                const float lse2 = cref + lg2f(v);
+                                float norm2 = lse2;
+                                if (norm_eps_on != 0.f) {          // gmm_impl.py:113  log(sum exp + 1e-8)
+                                    const float Mx = fmaxf(lse2, kLog2Eps8);
+                                    norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
+                                    inv *= ex2f(lse2 - norm2);
+                                }
+                                if (sw == 0) {
+                                    ll += (double)(norm2 * kLn2);
+                                    nlive += 1.0;
+                                }
+                            }
+                        }
+                        fin[warp][lane] = make_float2(inv, inv);
+                    }
+                    const unsigned any_under = __ballot_sync(0xffffffffu, under);
+                    if (any_under) {
+                        // ---------------- rare path: exact per-point maximum, own scratch + classic group barriers
+                        float mx[PB], sm2[PB];
+#pragma unroll
+                        for (int p = 0; p < PB; ++p) {
+                            const int ip = min(bc + p, cn - 1);
+                            const float4 P0 = spts[ip][0], P1 = spts[ip][1];
+                            float2 dx, dy, dz;
+                            const float2 q = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
+                            e[u][p] = q;
+                            mx[p] = fmaxf(fmaxf(q.x, q.y), kNegBig);
+                        }
+                        reduce_scatter<PB>(mx, lane, true);
+                        group_bar3(1 + g, gthreads);               // scratch free (previous rare batch fully consumed)
+                        if (rwriter) redslow[g][ridx][sw] = mx[0];
+                        group_bar3(1 + g, gthreads);
+                        if (sw == 0 && lane < PB) {
+                            float v = kNegBig;
+                            for (int w = 0; w < Sdiv; ++w) v = fmaxf(v, redslow[g][lane][w]);
+                            finmax[g][lane] = v;
+                        }
+                        group_bar3(1 + g, gthreads);
+#pragma unroll
+                        for (int p = 0; p < PB; ++p) {
+                            const float m = finmax[g][p];
+                            e[u][p] = make_float2(ex2f(e[u][p].x - m), ex2f(e[u][p].y - m));
+                            sm2[p] = e[u][p].x + e[u][p].y;
+                        }
+                        reduce_scatter<PB>(sm2, lane, false);
+                        if (rwriter) redslow[g][ridx][sw] = sm2[0];
+                        group_bar3(1 + g, gthreads);
+                        {
+                            float v = 0.f;
+                            if (lane < PB) {
+                                for (int w = 0; w < Sdiv; ++w) v += redslow[g][lane][w];
+                            }
+                            const float m = lane < PB ? finmax[g][lane] : 0.f;
+                            const bool valid = lane < np;
+                            float inv = 0.f;
+                            if (valid && v > 0.f && m > kNegBig) {
+                                const float lse2 = cref + m + lg2f(v);
+                                float norm2 = lse2, scale = 1.0f;
+                                if (norm_eps_on != 0.f) {
+                                    const float Mx = fmaxf(lse2, kLog2Eps8);
+                                    norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
+                                    scale = ex2f(lse2 - norm2);
+                                }
+                                inv = scale / v;
+                                if (sw == 0 && under) {
+                                    ll += (double)(norm2 * kLn2);
+                                    nlive += 1.0;
+                                }
+                            } else if (valid && under && sw == 0 && norm_eps_on != 0.f) {
+                                ll += (double)(kLog2Eps8 * kLn2);
+                            }
+                            if (lane < PB) fin[warp][lane] = make_float2(inv, inv);
+                        }
+                    }
+                    __syncwarp();
+                    // ---------------- pass 2: moments of the current batch
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) {
+                        const int ip = min(bc + p, cn - 1);
+                        const float4 P0 = spts[ip][0], P1 = spts[ip][1];
+                        const float2 inv2 = fin[warp][p];
+                        const float2 gam = fmul2(e[u][p], inv2);
+                        const float2 dx = fadd2(make_float2(P0.x, P0.y), k.nmx);
+                        const float2 dy = fadd2(make_float2(P0.z, P0.w), k.nmy);
+                        const float2 dz = fadd2(make_float2(P1.x, P1.y), k.nmz);
+                        const float2 gx = fmul2(gam, dx), gy = fmul2(gam, dy), gz = fmul2(gam, dz);
+                        a[0] = fadd2(a[0], gam);
+                        a[1] = fadd2(a[1], gx);
+                        a[2] = fadd2(a[2], gy);
+                        a[3] = fadd2(a[3], gz);
+                        a[4] = ffma2(gx, dx, a[4]);
+                        a[5] = ffma2(gx, dy, a[5]);
+                        a[6] = ffma2(gx, dz, a[6]);
+                        a[7] = ffma2(gy, dy, a[7]);
+                        a[8] = ffma2(gy, dz, a[8]);
+                        a[9] = ffma2(gz, dz, a[9]);
+                    }
+                    __syncwarp();
+                    ++kb;
+                }
+            }
+        }
+    }
+#undef HGMM_PASS1
+    const size_t row = (size_t)blockIdx.x * G + g;
+    float* dst = partial + row * (size_t)kMom * Jp;
+    if (live0) {
+        const int j = sw * 32 + lane;
+#pragma unroll
+        for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].x;
+    }
+    if (live1) {
+        const int j = (sw + Sdiv) * 32 + lane;
+#pragma unroll
+        for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].y;
+    }
+    if (sw == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ll += __shfl_xor_sync(0xffffffffu, ll, o);
+            nlive += __shfl_xor_sync(0xffffffffu, nlive, o);
+        }
+        if (lane == 0) {
+            rowaux[2 * row] = ll;
+            rowaux[2 * row + 1] = nlive;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // packed-FP32 peak probe (mode 2 of hgmm_measure_fp32_peak): 8 independent FFMA2 chains, register operands
 __global__ void __launch_bounds__(256) ffma2_peak_kernel(float* out, int iters, float seed, float bv, float cv) {
     float2 a0 = make_float2(seed, seed + 1), a1 = make_float2(seed + 2, seed + 3), a2 = make_float2(seed + 4, seed + 5),
@@ -422,7 +678,8 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
     // 72-register CTAs (71.5 vs 77.6 us on configs[1]); smaller CTAs co-reside 2-4 per SM.  one_cta_per_sm == 1 forces
     // the register-rich build, == 2 the two-CTA build (profiling switches).
     *big = (one_cta_per_sm == 1 || (one_cta_per_sm == 0 && w >= 8) || w > 13) ? 1 : 0;
-    int occ = *big ? occ_blocks(em_flat3_kernel<512, 1, 8, 1>, w * 32) : occ_blocks(em_flat3_kernel<416, 2, 4, 1>, w * 32);
+    if (one_cta_per_sm == 4 && w >= 8 && w <= 13) *big = 3;          // software-pipelined build (em_flat4_kernel)
+    int occ = *big == 3 ? 1 : *big ? occ_blocks(em_flat3_kernel<512, 1, 8, 1>, w * 32) : occ_blocks(em_flat3_kernel<416, 2, 4, 1>, w * 32);
     if (occ > 4) occ = 4;
     if (w >= 8 && occ > 2) occ = 2;
     int ctas = occ * num_sms;
@@ -437,7 +694,10 @@ cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int 
                             cudaStream_t s) {
     const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
     const int ncref = m.Jp / 32;
-    if (big == 2)
+    if (big == 3)
+        em_flat4_kernel<416><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux, done_flag,
+                                                     eps_on);
+    else if (big == 2)
         em_flat3_kernel<448, 1, 4, 2><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
                                                             done_flag, eps_on);
     else if (big)

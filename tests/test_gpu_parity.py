@@ -94,12 +94,12 @@ def test_flat_full_config2_matches_c_oracle(engine, bun000, J, sig):
         assert max(errs) < TOL, errs
 
 
-@pytest.mark.parametrize("variant,tile", [(0, 0), (0, 1), (0, 2), (0, 3), (3, 0), (2, 0), (2, 1), (1, 64), (1, 128), (1, 256), (1, 512)])
+@pytest.mark.parametrize("variant,tile", [(0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (3, 0), (2, 0), (2, 1), (1, 64), (1, 128), (1, 256), (1, 512)])
 def test_flat_kernel_variants_agree(engine, bun000, variant, tile):
     from oracle import flat_gmm
     X = bun000[::5]
     rng = np.random.default_rng(2)
-    J = 600 if tile == 3 else 96        # the two-team build needs >= 17 component slots
+    J = 600 if tile in (3, 4) else 96   # the two-team / pipelined builds need >= 17 component slots
     mu0 = X[rng.choice(len(X), J, replace=False)]
     cov0 = np.tile(np.eye(3, dtype=np.float32) * 2e-4, (J, 1, 1))
     engine.set_points(X)
