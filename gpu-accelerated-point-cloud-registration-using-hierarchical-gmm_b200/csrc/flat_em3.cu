@@ -679,7 +679,8 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
     // the register-rich build, == 2 the two-CTA build (profiling switches).
     *big = (one_cta_per_sm == 1 || (one_cta_per_sm == 0 && w >= 8) || w > 13) ? 1 : 0;
     if (one_cta_per_sm == 4 && w >= 8 && w <= 13) *big = 3;          // software-pipelined build (em_flat4_kernel)
-    int occ = *big == 3 ? 1 : *big ? occ_blocks(em_flat3_kernel<512, 1, 8, 1>, w * 32) : occ_blocks(em_flat3_kernel<416, 2, 4, 1>, w * 32);
+    if (one_cta_per_sm == 5 && w <= 13) *big = 4;                    // <=13 warps: register cap 152 instead of 128
+    int occ = *big >= 3 ? 1 : *big ? occ_blocks(em_flat3_kernel<512, 1, 8, 1>, w * 32) : occ_blocks(em_flat3_kernel<416, 2, 4, 1>, w * 32);
     if (occ > 4) occ = 4;
     if (w >= 8 && occ > 2) occ = 2;
     int ctas = occ * num_sms;
@@ -694,7 +695,10 @@ cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int 
                             cudaStream_t s) {
     const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
     const int ncref = m.Jp / 32;
-    if (big == 3)
+    if (big == 4)
+        em_flat3_kernel<416, 1, 8, 1><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,
+                                                            done_flag, eps_on);
+    else if (big == 3)
         em_flat4_kernel<416><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux, done_flag,
                                                      eps_on);
     else if (big == 2)

@@ -17,10 +17,16 @@ def load(build=True):
             subprocess.check_call(["make", "-C", os.path.join(_HERE, "c")], stdout=subprocess.DEVNULL)
         _lib = C.CDLL(_SO)
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_set_threads.argtypes = [C.c_int]
+        _lib.oracle_set_threads.restype = None
         _lib.oracle_flat_fit.restype = None
         _lib.oracle_flat_fit.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
     return _lib
+
+
+def set_threads(n):
+    load().oracle_set_threads(int(n))
 
 
 def num_threads():
