@@ -73,6 +73,9 @@ cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int 
                             int W, int Sdiv, int G, int grid, int big, float* partial, double* rowaux, const int* done_flag,
                             cudaStream_t s);
 cudaError_t launch_ffma2_peak(float* out, int blocks, int iters, cudaStream_t s);
+// flat_em5.cu (packed FP32, densities staged in shared memory per chunk of points)
+cudaError_t launch_em_flat5(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
+                            int W, int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s);
 
 // tree_em.cu
 void launch_tree_init(const TreeModel& t, const float* init_means, float sig2, cudaStream_t s);
