@@ -573,7 +573,16 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
     }
     const int S = Jp / 32;
     const int sdiv = (S + 1) / 2;                   // warps per group: each warp owns slots sw and sw + sdiv
-    if (one_cta_per_sm == 6 && sdiv >= 5 && sdiv <= 16) {        // shared-memory staged chunks (flat_em5.cu), one CTA per SM
+    if (one_cta_per_sm == 7 && S >= 8 && S <= 32) {              // one component per thread, staged chunks (flat_em6.cu)
+        int ctas = num_sms;
+        if ((long long)ctas * 16 > n) ctas = (n + 15) / 16;
+        if (ctas < 1) ctas = 1;
+        *W = S; *Sdiv = S; *G = 1; *grid = ctas; *big = 6;
+        return;
+    }
+    // shared-memory staged chunks (flat_em5.cu), one CTA per SM: measured faster than the per-batch-barrier kernels from
+    // 9 pair columns up (J > 512: 58.9 vs 67.6 us at J = 800, 49.9 vs 55.1 at J = 640; 37.2 vs 33.0 at J = 320)
+    if ((one_cta_per_sm == 6 && sdiv >= 5 && sdiv <= 16) || (one_cta_per_sm == 0 && sdiv >= 9 && sdiv <= 15)) {
         int ctas = num_sms;
         if ((long long)ctas * 16 > n) ctas = (n + 15) / 16;
         if (ctas < 1) ctas = 1;
@@ -604,6 +613,7 @@ cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int 
                             cudaStream_t s) {
     const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
     const int ncref = m.Jp / 32;
+    if (big == 6) return launch_em_flat6(x, y, z, n, m, cref_blocks, grid, partial, rowaux, done_flag, s);
     if (big == 5) return launch_em_flat5(x, y, z, n, m, cref_blocks, W, grid, partial, rowaux, done_flag, s);
     if (big == 4)
         em_flat3_kernel<416, 1, 8, 1><<<grid, W * 32, 0, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, Sdiv, G, partial, rowaux,

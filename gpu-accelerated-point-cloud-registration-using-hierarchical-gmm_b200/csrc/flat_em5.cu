@@ -2,33 +2,39 @@
 //
 // Same contract as em_flat3_kernel (expectationStep + maximizationStep of src/c++/gmm_fit/gmm_kernels.cu:278-350;
 // e_step + m_step of src/python/gmm_waymo/src/gmm_impl.py:90-116) and the same arithmetic per (point, component)
-// pair -- 12 packed operations for q2 and e = 2^(q2 - Cref), 17 for the ten centred moments -- but the
-// normalisation over J, which needs every warp of the CTA, is taken once per CHUNK of up to 56 points instead of
-// once per batch of 8: each lane parks its pair of e values for the whole chunk in a private shared-memory column
-// (conflict-free STS.64 / LDS.64, 8 B x threads x chunk points = up to 186 KB of the SM's 227 KB), so the CTA
-// meets at one barrier per chunk and both phases around it are long, barrier-free FFMA2 streams.
+// pair -- 12 packed operations for q2 and e = 2^(q2 - Cref), 17 for the ten centred moments.  Two things differ:
 //
-//   pass 1 (per batch of 8 points): q2, e -> ebuf[point][thread]; per-point partial sums -> register
-//                                   reduce-scatter -> red[chunk parity][point][warp]
-//   __syncthreads
-//   finish (every warp, redundantly, lanes = points): 1/sum, log-likelihood (warp 0), -> fin[warp][point]
-//   pass 2 (per point): gamma = e * 1/sum, ten centred moments in float2 registers
+// 1. The normalisation over J, which needs every warp of the CTA, is taken once per CHUNK of up to 64 points instead
+//    of once per batch of 8: each lane parks its pair of e values for the whole chunk in a private shared-memory
+//    column (conflict-free STS.64 / LDS.64; 8 B x columns x chunk points, up to ~190 KB of the SM's 227 KB), so both
+//    phases around the two chunk barriers are long, barrier-free FFMA2 streams.
+//
+//      pass 1 (batches of 8 points): q2, e -> ebuf[point][column]; per-point partial sums -> register
+//                                    reduce-scatter -> red[point][pair column]
+//      barrier; finish: warp w folds points w, w + W, ... (lane = pair column, xor-shuffle tree) -> inv[point]
+//      barrier; pass 2 (per point): gamma = e * inv, ten centred moments in float2 registers
+//
+// 2. Warps are spread evenly over the SM's four sub-partitions.  P = ceil(S/2) pair columns (S = Jp/32 slots) give
+//    P warps if every warp sweeps all points; at J = 800 that is 13 warps = 4+3+3+3, and the sub-partition with four
+//    runs 23 % longer than the mean (profiles/microbench/fp32_pipe.cu measures exactly 13/16 of the 16-warp rate).
+//    Here the P mod 4 left-over columns are each shared by 4 (or 2) warps that split the chunk's 8-point batches
+//    between them, so P = 4a + 1 or 4a + 2 runs 4a + 4 warps with identical load on every sub-partition; the
+//    sharing warps fold their partial moments through shared memory in a fixed order at the end.
 //
 // A chunk containing a point whose sum underflows the fixed reference (2^-100: further than ~11 sigma from every
-// component) is redone with an exact per-point maximum (two more barriers, CTA-uniform decision).
-// Partial moment rows + the fixed-order fp64 reduction are shared with flat_em2.cu / flat_em3.cu.
+// component) is redone with exact per-point maxima (CTA-uniform branch, four more barriers).
+// Every reduction has a fixed order: fits are bit-reproducible.
 #include "common.cuh"
 #include "kernels.h"
 #include "packed.cuh"
 
 namespace hgmm {
 
-constexpr int kMaxWarps5 = 16;
-
-// dynamic shared memory layout (CH = chunk points, multiple of 8; T = threads):
-//   float4 spts[kChunk3][2] | float red[2][CH][16] | float redslow[2][CH][16] | float2 fin[16][CH] | float2 ebuf[CH][T]
-__host__ __device__ inline size_t flat5_smem_bytes(int CH, int T) {
-    return (size_t)kChunk3 * 32 + (size_t)CH * (2 * 64 + 2 * 64 + 128) + (size_t)CH * T * 8;
+// dynamic shared memory layout (CH = chunk points, multiple of 8; C = 32 * pair columns):
+//   float4 spts[kChunk3][2] | float red[CH][16] | float2 inv[CH] | float mval[CH] | float uflag[CH] | double wsum[16][2]
+//   | int flags[4] | float2 ebuf[CH][C]
+__host__ __device__ inline size_t flat5_smem_bytes(int CH, int C) {
+    return (size_t)kChunk3 * 32 + (size_t)CH * (64 + 8 + 4 + 4) + 16 * 16 + 16 + (size_t)CH * C * 8;
 }
 
 template <int MAXT>
@@ -36,35 +42,50 @@ __global__ void __launch_bounds__(MAXT, 1) em_flat5_kernel(const float* __restri
                                                            const float* __restrict__ pz, int n,
                                                            const PackedComp* __restrict__ packed,
                                                            const float* __restrict__ cref_blocks, int n_cref, int J, int Jp,
-                                                           int W, int CH, float* __restrict__ partial,
+                                                           int P, int CH, float* __restrict__ partial,
                                                            double* __restrict__ rowaux, const int* __restrict__ done_flag,
                                                            float norm_eps_on) {
     if (*done_flag) return;
     constexpr int PB = 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = blockDim.x;
+    const int T = blockDim.x, W = T >> 5;
+    const int C = P * 32;                                                  // ebuf columns
     float4* spts = reinterpret_cast<float4*>(smem_raw);                    // [kChunk3][2]  (x,x,y,y) (z,z,0,0)
-    float* red = reinterpret_cast<float*>(spts + kChunk3 * 2);             // [2][CH][16]
-    float* redslow = red + 2 * CH * 16;                                    // [2][CH][16]   rare path: maxima | sums
-    float2* fin = reinterpret_cast<float2*>(redslow + 2 * CH * 16);        // [16][CH]      (inv, inv), private to each warp
-    float2* ebuf = fin + 16 * CH;                                          // [CH][T]       private column per thread
+    float* red = reinterpret_cast<float*>(spts + kChunk3 * 2);             // [CH][16]
+    float2* inv = reinterpret_cast<float2*>(red + CH * 16);                // [CH]  (inv, inv)
+    float* mval = reinterpret_cast<float*>(inv + CH);                      // [CH]  rare path: exact maxima
+    float* uflag = mval + CH;                                              // [CH]  1 = the fixed-reference sum underflowed
+    double* wsum = reinterpret_cast<double*>(uflag + CH);                  // [16][2]
+    int* flags = reinterpret_cast<int*>(wsum + 32);                        // [4]
+    float2* ebuf = reinterpret_cast<float2*>(flags + 4);                   // [CH][C]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 4 * CH * 16; i += T) red[i] = 0.f;              // warp slots >= W stay zero (red and redslow)
     const int S = Jp >> 5;
     const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     const bool rwriter = (lane & 3) == 0;
+    if (tid < 4) flags[tid] = 0;
 
-    float cref = -INFINITY;
-    for (int i = 0; i < n_cref; ++i) cref = fmaxf(cref, __ldg(cref_blocks + i));
+    // ---- which pair column, and which share of every chunk's batches, this warp sweeps
+    const int full = P == W ? P : (P & ~3);               // columns swept whole by one warp
+    int col = warp, nsplit = 1, sidx = 0;
+    if (warp >= full) {
+        const int r = P - full;                           // 1 or 2 left-over columns shared by the last 4 warps
+        nsplit = 4 / r;
+        col = full + (warp - full) / nsplit;
+        sidx = (warp - full) % nsplit;
+    }
+
+    float cref = lane < n_cref ? __ldg(cref_blocks + lane) : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cref = fmaxf(cref, __shfl_xor_sync(0xffffffffu, cref, o));
     if (!(cref > kNegBig)) cref = 0.f;
 
-    // ---- the lane's component pair -> registers: slots warp (low half) and warp + W (high half)
+    // ---- the lane's component pair -> registers: slots col (low half) and col + P (high half)
     PairParams k;
-    const bool live0 = warp < S, live1 = warp + W < S;
+    const bool live0 = col < S, live1 = col + P < S;
     {
-        const float4* a4 = reinterpret_cast<const float4*>(packed + (live0 ? warp * 32 + lane : 0));
-        const float4* b4 = reinterpret_cast<const float4*>(packed + (live1 ? (warp + W) * 32 + lane : 0));
+        const float4* a4 = reinterpret_cast<const float4*>(packed + (live0 ? col * 32 + lane : 0));
+        const float4* b4 = reinterpret_cast<const float4*>(packed + (live1 ? (col + P) * 32 + lane : 0));
         const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), a2 = __ldg(a4 + 2);
         const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1), b2 = __ldg(b4 + 2);
         k.nmx = make_float2(-a0.x, -b0.x);
@@ -81,13 +102,12 @@ __global__ void __launch_bounds__(MAXT, 1) em_flat5_kernel(const float* __restri
     float2 a[kMom];
 #pragma unroll
     for (int m = 0; m < kMom; ++m) a[m] = make_float2(0.f, 0.f);
-    double ll = 0.0, nlive = 0.0;                         // accumulated by the finishing lanes of warp 0
+    double ll = 0.0, nlive = 0.0;                         // lane 0 of every warp, for the points it finishes
 
     const int per = (int)(((long long)n + gridDim.x - 1) / gridDim.x);
     const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
     int parity = 0;
-    float2* ecol = ebuf + tid;                            // element p of the column is ecol[p * T]
-    float2* myfin = fin + warp * CH;
+    float2* ecol = ebuf + col * 32 + lane;                // element p of the column is ecol[p * C]
 
     for (int cb = lo; cb < hi; cb += kChunk3) {
         const int cn = min(kChunk3, hi - cb);
@@ -99,10 +119,12 @@ __global__ void __launch_bounds__(MAXT, 1) em_flat5_kernel(const float* __restri
         }
         __syncthreads();
         for (int c0 = 0; c0 < cn; c0 += CH) {
-            const int ch = min(CH, cn - c0);              // points of this chunk
-            float* redp = red + parity * CH * 16;
-            // ---------------- pass 1: e -> ebuf, per-point partial sums -> red[parity]
-            for (int b = 0; b < ch; b += PB) {
+            const int ch = min(CH, cn - c0);              // valid points of this chunk
+            const int nb = (ch + PB - 1) / PB;            // its 8-point batches
+            const int b_lo = (sidx * nb / nsplit) * PB, b_hi = ((sidx + 1) * nb / nsplit) * PB;   // this warp's share
+            const int p_hi = min(b_hi, ch);
+            // ---------------- pass 1: e -> ebuf, per-point partial sums -> red
+            for (int b = b_lo; b < b_hi; b += PB) {
                 float sm[PB];
                 float2 q[PB];
                 // all shared-memory loads of the batch first: the compiler must keep an LDS behind an earlier STS it cannot
@@ -117,51 +139,44 @@ __global__ void __launch_bounds__(MAXT, 1) em_flat5_kernel(const float* __restri
 #pragma unroll
                 for (int p = 0; p < PB; ++p) {
                     const float2 e = make_float2(ex2f(q[p].x), ex2f(q[p].y));
-                    ecol[(size_t)(b + p) * T] = e;
+                    ecol[(size_t)(b + p) * C] = e;
                     sm[p] = e.x + e.y;
                 }
                 reduce_scatter<PB>(sm, lane, false);
-                if (rwriter) redp[(b + ridx) * 16 + warp] = sm[0];
+                if (rwriter) red[(b + ridx) * 16 + col] = sm[0];
             }
             __syncthreads();
-            // ---------------- finish: every warp folds all the chunk's sums itself (lane = point, two rounds for CH > 32)
-            unsigned under_mask = 0;                      // bit r: this lane's point of round r underflowed
+            // ---------------- finish: warp w folds the partial sums of points w, w + W, ... (lane = pair column)
+            for (int pt = warp; pt < nb * PB; pt += W) {
+                float v = lane < P ? red[pt * 16 + lane] : 0.f;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int pp = lane + 32 * r;
-                if (pp < CH) {
-                    const float4* r4 = reinterpret_cast<const float4*>(redp + pp * 16);
-                    const float4 r0 = r4[0], r1 = r4[1], r2 = r4[2], r3 = r4[3];
-                    const float v = (((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w))) +
-                                    (((r2.x + r2.y) + (r2.z + r2.w)) + ((r3.x + r3.y) + (r3.z + r3.w)));
-                    const bool valid = pp < ch;
+                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) {
+                    const bool valid = pt < ch;
                     const bool under = valid && !(v >= kUnder3);
-                    if (under) under_mask |= 1u << r;
-                    float inv = (valid && !under) ? __fdividef(1.0f, v) : 0.f;
-                    if (norm_eps_on != 0.f || warp == 0) {   // only the PY flavour rescales; only warp 0 keeps the log-lik
-                        if (valid && !under) {
-                            const float lse2 = cref + lg2f(v);
-                            float norm2 = lse2;
-                            if (norm_eps_on != 0.f) {        // gmm_impl.py:113  log(sum exp + 1e-8)
-                                const float Mx = fmaxf(lse2, kLog2Eps8);
-                                norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
-                                inv *= ex2f(lse2 - norm2);
-                            }
-                            if (warp == 0) {
-                                ll += (double)(norm2 * kLn2);
-                                nlive += 1.0;
-                            }
+                    float iv = (valid && !under) ? __fdividef(1.0f, v) : 0.f;
+                    if (valid && !under) {
+                        const float lse2 = cref + lg2f(v);
+                        float norm2 = lse2;
+                        if (norm_eps_on != 0.f) {            // gmm_impl.py:113  log(sum exp + 1e-8)
+                            const float Mx = fmaxf(lse2, kLog2Eps8);
+                            norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
+                            iv *= ex2f(lse2 - norm2);
                         }
+                        ll += (double)(norm2 * kLn2);
+                        nlive += 1.0;
                     }
-                    myfin[pp] = make_float2(inv, inv);
+                    inv[pt] = make_float2(iv, iv);
+                    uflag[pt] = under ? 1.f : 0.f;
+                    if (under) flags[parity] = 1;
                 }
             }
-            const unsigned any_under = __ballot_sync(0xffffffffu, under_mask != 0);   // identical in every warp (same data, same order)
+            __syncthreads();
+            const bool any_under = flags[parity] != 0;
+            if (tid == 0) flags[parity ^ 1] = 0;          // the next chunk's flag; its last readers are past the barrier above
             if (any_under) {
-                // ---------------- rare path: exact per-point maximum for the whole chunk
-                float* rmax = redslow;
-                float* rsum = redslow + CH * 16;
-                for (int b = 0; b < ch; b += PB) {
+                // ---------------- rare path: exact per-point maxima for the whole chunk (CTA-uniform branch)
+                for (int b = b_lo; b < b_hi; b += PB) {
                     float mx[PB];
 #pragma unroll
                     for (int p = 0; p < PB; ++p) {
@@ -172,39 +187,48 @@ __global__ void __launch_bounds__(MAXT, 1) em_flat5_kernel(const float* __restri
                         mx[p] = fmaxf(fmaxf(q.x, q.y), kNegBig);
                     }
                     reduce_scatter<PB>(mx, lane, true);
-                    if (rwriter) rmax[(b + ridx) * 16 + warp] = mx[0];
+                    if (rwriter) red[(b + ridx) * 16 + col] = mx[0];
                 }
                 __syncthreads();
-                for (int b = 0; b < ch; b += PB) {
+                for (int pt = warp; pt < nb * PB; pt += W) {
+                    float v = lane < P ? red[pt * 16 + lane] : kNegBig;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                    if (lane == 0) mval[pt] = v;
+                }
+                __syncthreads();
+                for (int b = b_lo; b < b_hi; b += PB) {
                     float sm[PB];
+                    float2 q[PB];
 #pragma unroll
                     for (int p = 0; p < PB; ++p) {
                         const int ip = min(c0 + b + p, cn - 1);
                         const float4 P0 = spts[2 * ip], P1 = spts[2 * ip + 1];
-                        float m = kNegBig;
-                        for (int w = 0; w < W; ++w) m = fmaxf(m, rmax[(b + p) * 16 + w]);
                         float2 dx, dy, dz;
-                        const float2 q = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
-                        const float2 e = make_float2(ex2f(q.x - m), ex2f(q.y - m));
-                        ecol[(size_t)(b + p) * T] = e;
+                        q[p] = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
+                        const float m = mval[b + p];
+                        q[p].x -= m;
+                        q[p].y -= m;
+                    }
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) {
+                        const float2 e = make_float2(ex2f(q[p].x), ex2f(q[p].y));
+                        ecol[(size_t)(b + p) * C] = e;
                         sm[p] = e.x + e.y;
                     }
                     reduce_scatter<PB>(sm, lane, false);
-                    if (rwriter) rsum[(b + ridx) * 16 + warp] = sm[0];
+                    if (rwriter) red[(b + ridx) * 16 + col] = sm[0];
                 }
                 __syncthreads();
+                for (int pt = warp; pt < nb * PB; pt += W) {
+                    float v = lane < P ? red[pt * 16 + lane] : 0.f;
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int pp = lane + 32 * r;
-                    if (pp < CH) {
-                        float v = 0.f, m = kNegBig;
-                        for (int w = 0; w < W; ++w) {
-                            v += rsum[pp * 16 + w];
-                            m = fmaxf(m, rmax[pp * 16 + w]);
-                        }
-                        const bool valid = pp < ch;
-                        const bool under = (under_mask >> r) & 1u;
-                        float inv = 0.f;
+                    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) {
+                        const bool valid = pt < ch;
+                        const bool under = uflag[pt] != 0.f;
+                        const float m = mval[pt];
+                        float iv = 0.f;
                         if (valid && v > 0.f && m > kNegBig) {
                             const float lse2 = cref + m + lg2f(v);
                             float norm2 = lse2, scale = 1.0f;
@@ -213,25 +237,25 @@ __global__ void __launch_bounds__(MAXT, 1) em_flat5_kernel(const float* __restri
                                 norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
                                 scale = ex2f(lse2 - norm2);
                             }
-                            inv = scale / v;
-                            if (warp == 0 && under) {         // the fast path left only the underflowed points out
+                            iv = scale / v;
+                            if (under) {                     // the fast path left only the underflowed points out
                                 ll += (double)(norm2 * kLn2);
                                 nlive += 1.0;
                             }
-                        } else if (valid && under && warp == 0 && norm_eps_on != 0.f) {
+                        } else if (valid && under && norm_eps_on != 0.f) {
                             ll += (double)(kLog2Eps8 * kLn2);  // log(0 + 1e-8)
                         }
-                        myfin[pp] = make_float2(inv, inv);
+                        inv[pt] = make_float2(iv, iv);
                     }
                 }
+                __syncthreads();
             }
-            __syncwarp();
-            // ---------------- pass 2: moments
+            // ---------------- pass 2: moments of this warp's share of the chunk
 #pragma unroll 4
-            for (int p = 0; p < ch; ++p) {
+            for (int p = b_lo; p < p_hi; ++p) {
                 const int ip = c0 + p;
                 const float4 P0 = spts[2 * ip], P1 = spts[2 * ip + 1];
-                const float2 gam = fmul2(ecol[(size_t)p * T], myfin[p]);
+                const float2 gam = fmul2(ecol[(size_t)p * C], inv[p]);
                 const float2 dx = fadd2(make_float2(P0.x, P0.y), k.nmx);
                 const float2 dy = fadd2(make_float2(P0.z, P0.w), k.nmy);
                 const float2 dz = fadd2(make_float2(P1.x, P1.y), k.nmz);
@@ -247,44 +271,69 @@ __global__ void __launch_bounds__(MAXT, 1) em_flat5_kernel(const float* __restri
                 a[8] = ffma2(gy, dz, a[8]);
                 a[9] = ffma2(gz, dz, a[9]);
             }
-            __syncwarp();                                  // fin[warp] is rewritten by the next chunk's finishing lanes
             parity ^= 1;
         }
     }
+    // ---- warps sharing a column fold their partial moments in a fixed order (the e buffer is free now)
+    __syncthreads();
+    if (nsplit > 1 && sidx > 0) {
+        float2* scratch = ebuf + ((size_t)(col - full) * 3 + (sidx - 1)) * 32 * kMom;
+#pragma unroll
+        for (int m = 0; m < kMom; ++m) scratch[m * 32 + lane] = a[m];
+    }
+    if (lane == 0) {
+        wsum[2 * warp] = ll;
+        wsum[2 * warp + 1] = nlive;
+    }
+    __syncthreads();
+    if (nsplit > 1 && sidx == 0) {
+        for (int s2 = 1; s2 < nsplit; ++s2) {
+            const float2* scratch = ebuf + ((size_t)(col - full) * 3 + (s2 - 1)) * 32 * kMom;
+#pragma unroll
+            for (int m = 0; m < kMom; ++m) a[m] = fadd2(a[m], scratch[m * 32 + lane]);
+        }
+    }
     // ---- partial rows: partial[row][m][Jp], row = blockIdx
-    float* dst = partial + (size_t)blockIdx.x * kMom * Jp;
-    if (live0) {
-        const int j = warp * 32 + lane;
+    if (sidx == 0) {
+        float* dst = partial + (size_t)blockIdx.x * kMom * Jp;
+        if (live0) {
+            const int j = col * 32 + lane;
 #pragma unroll
-        for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].x;
-    }
-    if (live1) {
-        const int j = (warp + W) * 32 + lane;
-#pragma unroll
-        for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].y;
-    }
-    if (warp == 0) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ll += __shfl_xor_sync(0xffffffffu, ll, o);
-            nlive += __shfl_xor_sync(0xffffffffu, nlive, o);
+            for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].x;
         }
-        if (lane == 0) {
-            rowaux[2 * blockIdx.x] = ll;
-            rowaux[2 * blockIdx.x + 1] = nlive;
+        if (live1) {
+            const int j = (col + P) * 32 + lane;
+#pragma unroll
+            for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].y;
         }
+    }
+    if (tid == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int w = 0; w < W; ++w) {
+            s0 += wsum[2 * w];
+            s1 += wsum[2 * w + 1];
+        }
+        rowaux[2 * blockIdx.x] = s0;
+        rowaux[2 * blockIdx.x + 1] = s1;
     }
 }
 
-// chunk length for T threads: as many points as fit the opt-in shared-memory limit (a multiple of 8, at most 64)
-int flat5_chunk(int T, int smem_optin) {
+// warps for P pair columns: the P mod 4 = 1 or 2 left-over columns are shared by four warps (see the header)
+int flat5_warps(int P) {
+    const int r = P & 3;
+    if ((r == 1 || r == 2) && (P & ~3) + 4 <= 16) return (P & ~3) + 4;
+    return P;
+}
+
+// chunk length for C columns: as many points as fit the opt-in shared-memory limit (a multiple of 8, at most 64)
+static int flat5_chunk(int C, int smem_optin) {
     int ch = 64;
-    while (ch > 8 && flat5_smem_bytes(ch, T) > (size_t)smem_optin) ch -= 8;
+    while (ch > 8 && flat5_smem_bytes(ch, C) > (size_t)smem_optin) ch -= 8;
     return ch;
 }
 
 cudaError_t launch_em_flat5(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
-                            int W, int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s) {
+                            int P, int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s) {
     static int smem_optin = 0;
     if (!smem_optin) {
         int dev = 0;
@@ -294,17 +343,18 @@ cudaError_t launch_em_flat5(const float* x, const float* y, const float* z, int 
         cudaFuncSetAttribute(em_flat5_kernel<416>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
         cudaFuncSetAttribute(em_flat5_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
     }
-    if (W < 1 || W > kMaxWarps5) return cudaErrorInvalidValue;
+    if (P < 1 || P > 16) return cudaErrorInvalidValue;
     const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
     const int ncref = m.Jp / 32;
+    const int W = flat5_warps(P);
     const int T = W * 32;
-    const int CH = flat5_chunk(T, smem_optin);
-    const size_t smem = flat5_smem_bytes(CH, T);
+    const int CH = flat5_chunk(P * 32, smem_optin);
+    const size_t smem = flat5_smem_bytes(CH, P * 32);
     if (W <= 13)
-        em_flat5_kernel<416><<<grid, T, smem, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, W, CH, partial, rowaux, done_flag,
+        em_flat5_kernel<416><<<grid, T, smem, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, P, CH, partial, rowaux, done_flag,
                                                     eps_on);
     else
-        em_flat5_kernel<512><<<grid, T, smem, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, W, CH, partial, rowaux, done_flag,
+        em_flat5_kernel<512><<<grid, T, smem, s>>>(x, y, z, n, m.packed, cref_blocks, ncref, m.J, m.Jp, P, CH, partial, rowaux, done_flag,
                                                     eps_on);
     return cudaGetLastError();
 }

@@ -77,6 +77,10 @@ cudaError_t launch_ffma2_peak(float* out, int blocks, int iters, cudaStream_t s)
 cudaError_t launch_em_flat5(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
                             int W, int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s);
 
+// flat_em6.cu (one component per thread, densities staged in shared memory)
+cudaError_t launch_em_flat6(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
+                            int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s);
+
 // tree_em.cu
 void launch_tree_init(const TreeModel& t, const float* init_means, float sig2, cudaStream_t s);
 void launch_tree_pack_all(const TreeModel& t, cudaStream_t s);

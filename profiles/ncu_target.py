@@ -9,12 +9,13 @@ eng = hgmm_b200.Engine(0)
 if what == "flat":
     X = np.load(os.path.join(ROOT, "tests/golden/bun000_xyz.npy"))
     J = int(sys.argv[2]) if len(sys.argv) > 2 else 800
+    tile = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     rng = np.random.default_rng(1)
     mu0 = X[rng.choice(len(X), J, replace=False)]
     cov0 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J, 1, 1)); w0 = np.full(J, 1 / J, np.float32)
     eng.set_points(torch.from_numpy(X).cuda())
     for _ in range(3):
-        eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False)
+        eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False, tile_points=tile)
 elif what == "reg":
     from hgmm_b200 import hgmm as H
     S = np.load(os.path.join(ROOT, "tests/golden/bun000_xyz.npy")); T = np.load(os.path.join(ROOT, "tests/golden/bun045_xyz.npy"))

@@ -94,12 +94,12 @@ def test_flat_full_config2_matches_c_oracle(engine, bun000, J, sig):
         assert max(errs) < TOL, errs
 
 
-@pytest.mark.parametrize("variant,tile", [(0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (3, 0), (2, 0), (2, 1), (1, 64), (1, 128), (1, 256), (1, 512)])
+@pytest.mark.parametrize("variant,tile", [(0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (0, 6), (0, 7), (3, 0), (2, 0), (2, 1), (1, 64), (1, 128), (1, 256), (1, 512)])
 def test_flat_kernel_variants_agree(engine, bun000, variant, tile):
     from oracle import flat_gmm
     X = bun000[::5]
     rng = np.random.default_rng(2)
-    J = 600 if tile in (3, 4) else 96   # the two-team / pipelined builds need >= 17 component slots
+    J = 600 if tile in (3, 4, 6, 7) else 96   # the two-team / pipelined builds need >= 17 component slots
     mu0 = X[rng.choice(len(X), J, replace=False)]
     cov0 = np.tile(np.eye(3, dtype=np.float32) * 2e-4, (J, 1, 1))
     engine.set_points(X)
@@ -108,68 +108,75 @@ def test_flat_kernel_variants_agree(engine, bun000, variant, tile):
     assert rel_fro(r["means"], omu) < TOL and rel_fro(r["covs"], ocov) < TOL and rel_fro(r["weights"], ow) < TOL
 
 
-@pytest.mark.parametrize("J", [160, 161, 320, 545, 800, 1024])
-def test_flat_staged_kernel_matches_oracle(engine, bun000, J):
-    """flat_em5.cu (densities staged in shared memory, one barrier per chunk): every warp count 5..16, ragged J and a
-    cloud whose per-CTA share is not a multiple of the chunk or of the 8-point batch"""
+STAGED = [(6, 160), (6, 161), (6, 320), (6, 545), (6, 800), (6, 1024), (7, 225), (7, 256), (7, 320), (7, 545), (7, 800), (7, 1024)]
+
+
+@pytest.mark.parametrize("tile,J", STAGED)
+def test_flat_staged_kernel_matches_oracle(engine, bun000, tile, J):
+    """flat_em5.cu / flat_em6.cu (densities staged in shared memory, tile_points = 6: component pair per lane, packed FP32;
+    7: one component per thread): every warp count, ragged J and a cloud whose per-CTA share is not a multiple of the
+    chunk or of the 8-point batch"""
     from oracle import flat_gmm
     X = bun000[::3][:13001]
     rng = np.random.default_rng(J)
     mu0 = X[rng.choice(len(X), J, replace=False)]
     cov0 = np.tile(np.eye(3, dtype=np.float32) * 3e-4, (J, 1, 1))
     engine.set_points(X)
-    r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=3, tile_points=6)
+    r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=3, tile_points=tile)
     ow, omu, ocov, oll = flat_gmm.cpp_fit(X, mu0, 3, sigma0_sq=np.float32(3e-4))
     assert rel_fro(r["means"], omu) < TOL and rel_fro(r["covs"], ocov) < TOL and rel_fro(r["weights"], ow) < TOL
     assert rel_fro(r["ll"], oll) < TOL
-    r2 = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=3, tile_points=6)
+    r2 = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=3, tile_points=tile)
     assert np.array_equal(r["means"], r2["means"]) and np.array_equal(r["covs"], r2["covs"])       # bit-reproducible
 
 
-def test_flat_staged_kernel_small_and_large_clouds(engine, bun000):
+@pytest.mark.parametrize("tile", [6, 7])
+def test_flat_staged_kernel_small_and_large_clouds(engine, bun000, tile):
     """fewer points than CTAs x 16 (short grid), and more than 512 points per CTA (several staging rounds)"""
     from oracle import flat_gmm
-    J = 200
+    J = 260
     for X in (bun000[::40], np.concatenate([bun000, bun000[::2] + np.float32(1e-4), bun000[::3] - np.float32(1e-4)])):
         rng = np.random.default_rng(7)
         mu0 = X[rng.choice(len(X), J, replace=False)]
         cov0 = np.tile(np.eye(3, dtype=np.float32) * 3e-4, (J, 1, 1))
         engine.set_points(X)
-        r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=3, tile_points=6)
+        r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=3, tile_points=tile)
         ow, omu, ocov, oll = flat_gmm.cpp_fit(X, mu0, 3, sigma0_sq=np.float32(3e-4))
         assert rel_fro(r["means"], omu) < TOL and rel_fro(r["covs"], ocov) < TOL and rel_fro(r["weights"], ow) < TOL
         assert rel_fro(r["ll"], oll) < TOL
 
 
+@pytest.mark.parametrize("tile", [6, 7])
 @pytest.mark.parametrize("cov_type", ["diag", "spherical"])
-def test_flat_staged_kernel_py_flavour(engine, bun000, cov_type):
-    """gmm_impl.py semantics (log(sum exp + 1e-8), +1e-6 floors) through the staged kernel, J = 200"""
+def test_flat_staged_kernel_py_flavour(engine, bun000, cov_type, tile):
+    """gmm_impl.py semantics (log(sum exp + 1e-8), +1e-6 floors) through the staged kernels, J = 260"""
     from oracle import flat_gmm
     X = bun000[::4]
-    J = 200
+    J = 260
     rng = np.random.default_rng(11)
     mu0 = X[rng.choice(len(X), J, replace=False)]
     cov0 = np.full((J, 3) if cov_type == "diag" else (J,), 1e-3, np.float32)
     w0 = np.full(J, 1 / J, np.float32)
     engine.set_points(X)
-    r = engine.fit_flat(mu0, cov0, w0, cov_type=cov_type, max_iter=5, tol=0.0, tile_points=6)
+    r = engine.fit_flat(mu0, cov0, w0, cov_type=cov_type, max_iter=5, tol=0.0, tile_points=tile)
     o = flat_gmm.py_train_gmm(X, 5, 0.0, mu0, cov0, w0, cov_type)
     assert rel_fro(r["means"], o[1]) < TOL and rel_fro(r["weights"], o[2]) < TOL and rel_fro(r["covs"], o[3]) < TOL
     assert rel_fro(r["ll"], o[4]) < TOL
 
 
-def test_flat_staged_kernel_far_points(engine):
-    """the staged kernel's exact (max-shifted) path: 30-60 sigma outliers inside otherwise ordinary chunks"""
+@pytest.mark.parametrize("tile", [6, 7])
+def test_flat_staged_kernel_far_points(engine, tile):
+    """the staged kernels' exact (max-shifted) path: 30-60 sigma outliers inside otherwise ordinary chunks"""
     from oracle import flat_gmm
     rng = np.random.default_rng(4)
     X = np.concatenate([rng.normal(0, 0.01, (3000, 3)), rng.normal(0, 0.01, (3000, 3)) + [1.0, 0, 0],
                         [[0.5, 0.3, 0.0], [0.45, -0.2, 0.1], [0.3, 0.3, 0.3]]]).astype(np.float32)
-    J = 192
+    J = 288
     mu0 = X[rng.choice(len(X) - 3, J, replace=False)]          # never an outlier
     X = X[rng.permutation(len(X))]
     cov0 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J, 1, 1))
     engine.set_points(X)
-    r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=2, tile_points=6)
+    r = engine.fit_flat(mu0, cov0, np.full(J, 1 / J, np.float32), cov_type="full", max_iter=2, tile_points=tile)
     ow, omu, ocov, oll = flat_gmm.cpp_fit(X, mu0, 2, sigma0_sq=np.float32(1e-4))
     assert rel_fro(r["weights"], ow) < TOL and rel_fro(r["means"], omu) < TOL
     assert rel_fro(r["covs"], ocov) < TOL and rel_fro(r["ll"], oll) < TOL
