@@ -135,6 +135,10 @@ struct hgmm_ctx {
     bool have_target = false;
     bool have_racc = false;
 
+    // L2 registration of two flat mixtures
+    DevBuf l2buf;
+    int l2_js = 0, l2_jt = 0;
+
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -224,7 +228,7 @@ int hgmm_destroy(hgmm_ctx* ctx) {
                      &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->done_at, &ctx->partial, &ctx->rowaux, &ctx->cref, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
                      &ctx->t_cplx, &ctx->t_packed, &ctx->t_init, &ctx->p_group, &ctx->p_tilecnt, &ctx->p_tileoff, &ctx->p_segbase,
                      &ctx->p_seg0, &ctx->p_seg1, &ctx->p_chunkcnt, &ctx->p_chunkoff, &ctx->nchunks, &ctx->current, &ctx->tx, &ctx->ty,
-                     &ctx->tz, &ctx->racc, &ctx->Rt};
+                     &ctx->tz, &ctx->racc, &ctx->Rt, &ctx->l2buf};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < 2; ++i) {
         DevBuf* w[] = {&ctx->wx[i], &ctx->wy[i], &ctx->wz[i], &ctx->wperm[i], &ctx->wpnode[i], &ctx->wslot[i], &ctx->wcpar[i],
@@ -307,7 +311,9 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     if (cfg->max_iter < 0 || cfg->max_iter > 1000000) FAIL(HGMM_ERR_INVALID, "bad max_iter");
     if (cfg->flavor == HGMM_FLAVOR_CPP && cfg->cov_type != HGMM_COV_FULL) FAIL(HGMM_ERR_INVALID, "CPP flavour is full-covariance");
     if (cfg->flavor == HGMM_FLAVOR_PY && cfg->cov_type == HGMM_COV_FULL) FAIL(HGMM_ERR_INVALID, "PY flavour is diag/spherical");
-    if (cfg->flavor != HGMM_FLAVOR_CPP && cfg->flavor != HGMM_FLAVOR_PY) FAIL(HGMM_ERR_INVALID, "unknown flavor");
+    if (cfg->flavor == HGMM_FLAVOR_PY_OLD && cfg->cov_type != HGMM_COV_DIAG) FAIL(HGMM_ERR_INVALID, "PY_OLD flavour is diagonal");
+    if (cfg->flavor != HGMM_FLAVOR_CPP && cfg->flavor != HGMM_FLAVOR_PY && cfg->flavor != HGMM_FLAVOR_PY_OLD)
+        FAIL(HGMM_ERR_INVALID, "unknown flavor");
     CK(cudaSetDevice(ctx->device));
     const int Jp = (J + 31) / 32 * 32;
     const size_t ce = cov_elems(cfg->cov_type);
@@ -398,7 +404,7 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     if (out_means) CK(cudaMemcpyAsync(out_means, m.means, (size_t)J * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (out_covs) CK(cudaMemcpyAsync(out_covs, m.covs, (size_t)J * ce * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (out_weights) CK(cudaMemcpyAsync(out_weights, m.weights, (size_t)J * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (out_inv_cov && cfg->flavor == HGMM_FLAVOR_PY)
+    if (out_inv_cov && cfg->flavor != HGMM_FLAVOR_CPP)
         CK(cudaMemcpyAsync(out_inv_cov, m.inv_cov, (size_t)J * (ce == 1 ? 1 : 3) * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (out_ll && cfg->max_iter > 0)
         CK(cudaMemcpyAsync(out_ll, ctx->hist.p, (size_t)cfg->max_iter * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -766,6 +772,82 @@ int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, d
     ctx->last_ms[0] = ms; ctx->last_ms[1] = ms; ctx->last_ms[2] = 0;
     ctx->have_racc = false;       // the loop's solve kernel consumed (zeroed) the moments
     if (ctx->h_ctrl[2]) FAIL(HGMM_ERR_NUMERIC, "registration solve: singular / non-positive-definite system");
+    return HGMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// L2-distance registration of two flat mixtures (gmmreg_gpu/cost_functions.py, gmmreg.py:101-107)
+// device layout of l2buf (doubles): mu_s[3Js] | phi_s[Js] | mu_t[3Jt] | phi_t[Jt] | theta[8] | out[16]
+// ------------------------------------------------------------------------------------------
+int hgmm_l2_set_mixtures(hgmm_ctx* ctx, const double* mu_s, const double* phi_s, int32_t Js, const double* mu_t,
+                         const double* phi_t, int32_t Jt) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!mu_s || !phi_s || !mu_t || !phi_t) FAIL(HGMM_ERR_INVALID, "null mixture pointer");
+    if (Js < 1 || Jt < 1 || Js > 65536 || Jt > 65536) FAIL(HGMM_ERR_INVALID, "mixture sizes must be in [1, 65536]");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nd = 4 * (size_t)Js + 4 * (size_t)Jt + 24;
+    CK(ctx->l2buf.ensure(nd * sizeof(double)));
+    double* d = ctx->l2buf.as<double>();
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(d, mu_s, 3 * (size_t)Js * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + 3 * (size_t)Js, phi_s, (size_t)Js * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + 4 * (size_t)Js, mu_t, 3 * (size_t)Jt * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + 4 * (size_t)Js + 3 * (size_t)Jt, phi_t, (size_t)Jt * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->l2_js = Js;
+    ctx->l2_jt = Jt;
+    return HGMM_OK;
+}
+
+int hgmm_l2_cost_grad(hgmm_ctx* ctx, const double* theta, double sigma, double* out_f, double* out_grad) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (ctx->l2_js <= 0) FAIL(HGMM_ERR_STATE, "no mixtures: call hgmm_l2_set_mixtures first");
+    if (!theta || !(sigma > 0.0)) FAIL(HGMM_ERR_INVALID, "null theta / non-positive sigma");
+    CK(cudaSetDevice(ctx->device));
+    const size_t Js = ctx->l2_js, Jt = ctx->l2_jt;
+    double* d = ctx->l2buf.as<double>();
+    double* th = d + 4 * Js + 4 * Jt;
+    double* out = th + 8;
+    cudaStream_t s = ctx->stream;
+    for (int k = 0; k < 7; ++k) ctx->h_dbl[k] = theta[k];
+    CK(cudaMemcpyAsync(th, ctx->h_dbl, 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(launch_l2_cost_grad(d, d + 3 * Js, (int)Js, d + 4 * Js, d + 4 * Js + 3 * Jt, (int)Jt, th, sigma, out, s));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(ctx->h_dbl + 16, out, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (out_f) *out_f = ctx->h_dbl[16];
+    if (out_grad) for (int k = 0; k < 7; ++k) out_grad[k] = ctx->h_dbl[17 + k];
+    return HGMM_OK;
+}
+
+int hgmm_l2_optimize(hgmm_ctx* ctx, double* theta, double sigma, int32_t max_iter, double gtol, double* out_f,
+                     int32_t* out_iters, int32_t* out_nfev, int32_t* out_status) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (ctx->l2_js <= 0) FAIL(HGMM_ERR_STATE, "no mixtures: call hgmm_l2_set_mixtures first");
+    if (!theta || !(sigma > 0.0) || max_iter < 0 || max_iter > 100000) FAIL(HGMM_ERR_INVALID, "bad theta / sigma / max_iter");
+    CK(cudaSetDevice(ctx->device));
+    const size_t Js = ctx->l2_js, Jt = ctx->l2_jt;
+    double* d = ctx->l2buf.as<double>();
+    double* th = d + 4 * Js + 4 * Jt;
+    double* out = th + 8;
+    cudaStream_t s = ctx->stream;
+    for (int k = 0; k < 7; ++k) ctx->h_dbl[k] = theta[k];
+    CK(cudaMemcpyAsync(th, ctx->h_dbl, 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->ev0, s));
+    CK(launch_l2_bfgs(d, d + 3 * Js, (int)Js, d + 4 * Js, d + 4 * Js + 3 * Jt, (int)Jt, th, sigma, max_iter, gtol, out, s));
+    CK(cudaEventRecord(ctx->ev1, s));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(ctx->h_dbl + 8, th, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_dbl + 16, out, 11 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < 7; ++k) theta[k] = ctx->h_dbl[8 + k];
+    if (out_f) *out_f = ctx->h_dbl[16];
+    if (out_iters) *out_iters = (int32_t)ctx->h_dbl[17];
+    if (out_nfev) *out_nfev = (int32_t)ctx->h_dbl[18];
+    if (out_status) *out_status = (int32_t)ctx->h_dbl[19];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms[0] = ms; ctx->last_ms[1] = ms; ctx->last_ms[2] = 0;
     return HGMM_OK;
 }
 

@@ -80,15 +80,16 @@ __global__ void __launch_bounds__(128) flat_pack_kernel(FlatModel m, int first) 
     if (j < m.J) {
         const double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
         const double w = m.weights[j];
-        if (m.flavor == HGMM_FLAVOR_PY) {
+        if (m.flavor != HGMM_FLAVOR_CPP) {
+            const bool old = m.flavor == HGMM_FLAVOR_PY_OLD;     // gmmreg_gpu/gmm_impl.py: no 1e-6 floor, log(w) without eps
             double iv[3];
             for (int d = 0; d < 3; ++d) {
                 const double c = (m.cov_type == HGMM_COV_SPHERICAL) ? (double)m.covs[j] : (double)m.covs[3 * j + d];
-                iv[d] = first ? 1.0 / sqrt(c) : 1.0 / (sqrt(c + 1e-6) + 1e-8);
+                iv[d] = first ? 1.0 / sqrt(c) : (old ? 1.0 / (sqrt(c) + 1e-8) : 1.0 / (sqrt(c + 1e-6) + 1e-8));
                 if (m.cov_type == HGMM_COV_SPHERICAL) { if (d == 0) m.inv_cov[j] = (float)iv[0]; }
                 else m.inv_cov[3 * j + d] = (float)iv[d];
             }
-            p = pack_diag(log(w + 1e-8), mx, my, mz, iv[0], iv[1], iv[2], 3);
+            p = pack_diag(old ? log(w) : log(w + 1e-8), mx, my, mz, iv[0], iv[1], iv[2], 3);
         } else {
             const float* c = m.covs + 9 * j;
             Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
@@ -295,7 +296,27 @@ __device__ __forceinline__ float finalize_component(const FlatModel& m, int j, c
     const double M0 = A[0];
     const double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
     PackedComp p;
-    if (m.flavor == HGMM_FLAVOR_PY) {
+    if (m.flavor == HGMM_FLAVOR_PY_OLD) {
+        // gmmreg_gpu/gmm_impl.py:46-52,71: nk = sum g; mu = S1/(nk+eps); cov = clip(S2/(nk+eps) - mu^2, 0); pi = nk/N;
+        // inv_cov = 1/(sqrt(cov)+eps); log-weight without eps (:58).  S1, S2 rebuilt from the centred moments.
+        const double den = M0 + 1e-8;
+        const double mu0[3] = {mx, my, mz};
+        const double M2d[3] = {A[4], A[7], A[9]};
+        double mean[3], cov[3], iv[3];
+        for (int d = 0; d < 3; ++d) {
+            const double S1 = A[1 + d] + mu0[d] * M0;
+            const double S2 = M2d[d] + 2.0 * mu0[d] * A[1 + d] + mu0[d] * mu0[d] * M0;
+            mean[d] = S1 / den;
+            cov[d] = fmax(S2 / den - mean[d] * mean[d], 0.0);
+            iv[d] = 1.0 / (sqrt(cov[d]) + 1e-8);
+            m.covs[3 * j + d] = (float)cov[d];
+            m.inv_cov[3 * j + d] = (float)iv[d];
+            m.means[3 * j + d] = (float)mean[d];
+        }
+        const double w = M0 / n_total;
+        m.weights[j] = (float)w;
+        p = pack_diag(log((double)(float)w), (float)mean[0], (float)mean[1], (float)mean[2], iv[0], iv[1], iv[2], 3);
+    } else if (m.flavor == HGMM_FLAVOR_PY) {
         // gmm_impl.py:81-103 with S1 = sum g x, S2 = sum g x^2 rebuilt from the centred moments
         const double nk = M0 + 1e-8;
         const double S1[3] = {A[1] + mx * M0, A[2] + my * M0, A[3] + mz * M0};
@@ -349,9 +370,10 @@ __device__ __forceinline__ float finalize_component(const FlatModel& m, int j, c
 // stopping rule + bookkeeping of iteration `it` (one thread of the grid)
 __device__ __forceinline__ void finalize_bookkeeping(const FlatModel& m, double ll_sum, int* ctrl, int* done_at, int it,
                                                      double* ll_hist, double n_total) {
-    const double ll = (m.flavor == HGMM_FLAVOR_PY) ? ll_sum / n_total : ll_sum;
+    const bool py = m.flavor != HGMM_FLAVOR_CPP;
+    const double ll = py ? ll_sum / n_total : ll_sum;
     ll_hist[it] = ll;
-    const bool conv = (m.flavor == HGMM_FLAVOR_PY) && it > 0 && fabs(ll - ll_hist[it - 1]) < (double)m.tol;
+    const bool conv = py && it > 0 && fabs(ll - ll_hist[it - 1]) < (double)m.tol;
     done_at[it + 1] = conv ? 1 : 0;
     ctrl[1] = it + 1;
     ctrl[0] = conv ? 1 : 0;
@@ -606,7 +628,7 @@ static cudaError_t launch_em_flat_t(const float* x, const float* y, const float*
     if (occ < 1) occ = 1;
     int grid = nTiles < num_sms * occ ? nTiles : num_sms * occ;
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, smem, s>>>(x, y, z, n, m.packed, m.J, m.Jp, acc, ctrl, m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f);
+    kern<<<grid, 256, smem, s>>>(x, y, z, n, m.packed, m.J, m.Jp, acc, ctrl, m.flavor != HGMM_FLAVOR_CPP ? 1.f : 0.f);
     return cudaGetLastError();
 }
 

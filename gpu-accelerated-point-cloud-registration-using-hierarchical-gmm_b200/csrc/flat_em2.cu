@@ -367,7 +367,7 @@ void flat2_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* JT, int* W,
 cudaError_t launch_em_flat2(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
                             int JT, int W, int Sdiv, int G, int grid, int big, float* partial, double* rowaux,
                             const int* done_flag, cudaStream_t s) {
-    const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
+    const float eps_on = m.flavor != HGMM_FLAVOR_CPP ? 1.f : 0.f;
     const int ncref = m.Jp / 32;
     const int th = W * 32;
 #define HGMM_LAUNCH2(JTV, MAXT, MINB)                                                                                       \

@@ -611,7 +611,7 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
 cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
                             int W, int Sdiv, int G, int grid, int big, float* partial, double* rowaux, const int* done_flag,
                             cudaStream_t s) {
-    const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
+    const float eps_on = m.flavor != HGMM_FLAVOR_CPP ? 1.f : 0.f;
     const int ncref = m.Jp / 32;
     if (big == 6) return launch_em_flat6(x, y, z, n, m, cref_blocks, grid, partial, rowaux, done_flag, s);
     if (big == 5) return launch_em_flat5(x, y, z, n, m, cref_blocks, W, grid, partial, rowaux, done_flag, s);

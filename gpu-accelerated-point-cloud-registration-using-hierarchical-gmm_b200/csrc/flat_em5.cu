@@ -344,7 +344,7 @@ cudaError_t launch_em_flat5(const float* x, const float* y, const float* z, int 
         cudaFuncSetAttribute(em_flat5_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
     }
     if (P < 1 || P > 16) return cudaErrorInvalidValue;
-    const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
+    const float eps_on = m.flavor != HGMM_FLAVOR_CPP ? 1.f : 0.f;
     const int ncref = m.Jp / 32;
     const int W = flat5_warps(P);
     const int T = W * 32;

@@ -298,7 +298,7 @@ cudaError_t launch_em_flat6(const float* x, const float* y, const float* z, int 
     }
     const int W = m.Jp / 32;
     if (W < 1 || W > 32) return cudaErrorInvalidValue;
-    const float eps_on = m.flavor == HGMM_FLAVOR_PY ? 1.f : 0.f;
+    const float eps_on = m.flavor != HGMM_FLAVOR_CPP ? 1.f : 0.f;
     const int T = W * 32;
     const int CH = flat6_chunk(T, smem_optin);
     const size_t smem = flat6_smem_bytes(CH, T);

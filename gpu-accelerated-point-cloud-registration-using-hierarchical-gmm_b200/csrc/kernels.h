@@ -120,4 +120,10 @@ void launch_zero_doubles(double* p, size_t n, const int* ctrl, cudaStream_t s);
 void launch_fill_vbo(const float* x, const float* y, const float* z, int64_t n, int64_t offset, float* vbo_pos, float* vbo_col,
                      float scene_scale, float r, float g, float b, cudaStream_t s);
 
+// l2reg.cu (L2-distance registration of two flat mixtures, float64)
+cudaError_t launch_l2_cost_grad(const double* mu_s, const double* phi_s, int Js, const double* mu_t, const double* phi_t, int Jt,
+                                const double* theta, double sigma, double* out, cudaStream_t s);
+cudaError_t launch_l2_bfgs(const double* mu_s, const double* phi_s, int Js, const double* mu_t, const double* phi_t, int Jt,
+                           double* theta, double sigma, int max_iter, double gtol, double* out, cudaStream_t s);
+
 }  // namespace hgmm

@@ -6,6 +6,8 @@ Thin ctypes wrapper that keeps the reference's Python surface (SURVEY.md section
     gmm      : Feature, GMM_GPU, GMM_GPU_Base, GMM_CPU, GMM_CPU_Base (src/python/gmm_waymo/src/gmm.py)
     hgmm     : buildGMMTree, GMMTree, registration_gmmtree, RigidTransformation, EstepResult, MstepResult
                                                                      (src/python/hgmm/hgmm_gpu.py)
+    gmmreg   : registration_gmmreg, RigidGMMReg, L2DistRegistration, RigidCostFunction, GMM_GPU (older diag fitter)
+                                                                     (src/python/gmmreg_gpu/{gmmreg,cost_functions,gmm,gmm_impl}.py)
     dist     : point sharding + NCCL communicator bootstrap over torch.distributed
     engine   : Engine, the object wrapper over the C ABI (include/hgmm.h)
 
@@ -13,6 +15,6 @@ All compute runs in the CUDA library; there is no CPU fallback and nothing here 
 """
 from ._lib import HgmmError, LIB_PATH  # noqa: F401
 from .engine import Engine  # noqa: F401
-from . import gmm_impl, gmm, hgmm, dist  # noqa: F401
+from . import gmm_impl, gmm, hgmm, gmmreg, dist  # noqa: F401
 
-__all__ = ["Engine", "HgmmError", "gmm_impl", "gmm", "hgmm", "dist", "LIB_PATH"]
+__all__ = ["Engine", "HgmmError", "gmm_impl", "gmm", "hgmm", "gmmreg", "dist", "LIB_PATH"]

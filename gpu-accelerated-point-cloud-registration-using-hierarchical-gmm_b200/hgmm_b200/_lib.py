@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libhgmm.so")
 HGMM_OK = 0
 MEM_HOST, MEM_DEVICE = 0, 1
 COV_FULL, COV_DIAG, COV_SPHERICAL = 0, 1, 2
-FLAVOR_CPP, FLAVOR_PY = 0, 1
+FLAVOR_CPP, FLAVOR_PY, FLAVOR_PY_OLD = 0, 1, 2
 LL_LEVEL, LL_ESTEP = 0, 1
 SOLVER_TWIST_LSTSQ, SOLVER_PROCRUSTES = 0, 1
 
@@ -61,6 +61,9 @@ SIGNATURES = {
     "hgmm_reg_estep": (C.c_int, [_VP, _VP, _VP, C.c_float, _VP, _VP, _VP]),
     "hgmm_reg_mstep": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP]),
     "hgmm_register_tree": (C.c_int, [_VP, C.POINTER(RegConfig), _VP, _VP, _VP, _VP, _VP]),
+    "hgmm_l2_set_mixtures": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP, _VP, C.c_int32]),
+    "hgmm_l2_cost_grad": (C.c_int, [_VP, _VP, C.c_double, _VP, _VP]),
+    "hgmm_l2_optimize": (C.c_int, [_VP, _VP, C.c_double, C.c_int32, C.c_double, _VP, _VP, _VP, _VP]),
     "hgmm_fill_vbo": (C.c_int, [_VP, _VP, _VP, C.c_float, _VP, _VP]),
     "hgmm_comm_unique_id": (C.c_int, [_VP]),
     "hgmm_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),

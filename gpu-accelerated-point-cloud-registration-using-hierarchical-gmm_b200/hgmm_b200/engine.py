@@ -104,7 +104,7 @@ class Engine:
         o_means = np.empty((J, 3), np.float32) if want_outputs else None
         o_covs = np.empty(ce, np.float32) if want_outputs else None
         o_w = np.empty(J, np.float32) if want_outputs else None
-        o_inv = np.empty((J, 3) if ct == L.COV_DIAG else (J,), np.float32) if (want_outputs and flavor == L.FLAVOR_PY) else None
+        o_inv = np.empty((J, 3) if ct == L.COV_DIAG else (J,), np.float32) if (want_outputs and flavor != L.FLAVOR_CPP) else None
         o_ll = np.zeros(max(int(max_iter), 1), np.float64)
         o_it = np.zeros(1, np.int32)
         rc = self._lib.hgmm_fit_flat(self._ctx, C.byref(cfg), L.ptr(means), L.ptr(covs), L.ptr(weights), L.ptr(o_means),
@@ -188,6 +188,35 @@ class Engine:
         rc = self._lib.hgmm_register_tree(self._ctx, C.byref(cfg), L.ptr(rot), L.ptr(t), L.ptr(q), L.ptr(it), L.ptr(hist))
         self._check(rc, "hgmm_register_tree")
         return rot, t, float(q[0]), int(it[0]), hist[:int(it[0])]
+
+    # -- L2 registration of two flat mixtures ---------------------------------------------------
+    def l2_set_mixtures(self, mu_source, phi_source, mu_target, phi_target):
+        ms = np.ascontiguousarray(mu_source, np.float64).reshape(-1, 3)
+        ps = np.ascontiguousarray(phi_source, np.float64).reshape(-1)
+        mt = np.ascontiguousarray(mu_target, np.float64).reshape(-1, 3)
+        pt = np.ascontiguousarray(phi_target, np.float64).reshape(-1)
+        if len(ms) != len(ps) or len(mt) != len(pt):
+            raise ValueError("means / weights length mismatch")
+        rc = self._lib.hgmm_l2_set_mixtures(self._ctx, L.ptr(ms), L.ptr(ps), len(ps), L.ptr(mt), L.ptr(pt), len(pt))
+        self._check(rc, "hgmm_l2_set_mixtures")
+        return self
+
+    def l2_cost_grad(self, theta, sigma):
+        th = np.ascontiguousarray(theta, np.float64).reshape(7)
+        f = np.zeros(1)
+        g = np.zeros(7)
+        self._check(self._lib.hgmm_l2_cost_grad(self._ctx, L.ptr(th), float(sigma), L.ptr(f), L.ptr(g)), "hgmm_l2_cost_grad")
+        return float(f[0]), g
+
+    def l2_optimize(self, theta, sigma, max_iter=10, gtol=1.0e-5):
+        """-> (theta, f, iterations, evaluations, status)"""
+        th = np.array(theta, np.float64).reshape(7).copy()
+        f = np.zeros(1)
+        it, nf, st = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32)
+        rc = self._lib.hgmm_l2_optimize(self._ctx, L.ptr(th), float(sigma), int(max_iter), float(gtol), L.ptr(f), L.ptr(it),
+                                        L.ptr(nf), L.ptr(st))
+        self._check(rc, "hgmm_l2_optimize")
+        return th, float(f[0]), int(it[0]), int(nf[0]), int(st[0])
 
     def fill_vbo(self, vbo_pos_devptr, vbo_col_devptr, scene_scale=0.1):
         rc = self._lib.hgmm_fill_vbo(self._ctx, C.c_void_p(vbo_pos_devptr) if vbo_pos_devptr else None,

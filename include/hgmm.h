@@ -15,6 +15,7 @@
  *   hgmm_reg_mstep         GMMTree.maximization_step         src/python/hgmm/hgmm_gpu.py:729-752
  *   hgmm_register_tree     GMMTree.registration              src/python/hgmm/hgmm_gpu.py:754-768
  *                          GMMRegistration::pointCloudRegisterGPU (empty stub) gmm_reg.cu:54-56
+ *   hgmm_l2_*              RigidCostFunction / L2DistRegistration  src/python/gmmreg_gpu/cost_functions.py:29-69, gmmreg.py:62-121
  *   hgmm_fill_vbo          scanRegistration::copyBoidsToVBO  src/c++/gmm_fit/gmm_kernels.cu:532-542
  *                          GMMRegistration::copyBoidsToVBO   src/c++/gmm_registration/gmm_reg.cu:45-52
  *   hgmm_comm_*            (no reference counterpart: points sharded over ranks, one all-reduce of
@@ -53,7 +54,8 @@ extern "C" {
 
 /* which reference variant's EM semantics the flat fit follows (SURVEY.md section 7 compat table) */
 #define HGMM_FLAVOR_CPP 0          /* gmm_kernels.cu: full cov, pi = N_j/N, no regularisation, fixed iterations */
-#define HGMM_FLAVOR_PY 1           /* gmm_impl.py: diag/spherical, +1e-8 / +1e-6 terms, tol on mean log-lik */
+#define HGMM_FLAVOR_PY 1           /* gmm_waymo/src/gmm_impl.py: diag/spherical, +1e-8 / +1e-6 terms, tol on mean log-lik */
+#define HGMM_FLAVOR_PY_OLD 2       /* gmmreg_gpu/gmm_impl.py (the L2 registration's fitter): diag, clip(cov, 0), pi = nk/N */
 
 /* level log-likelihood used for the tree's convergence test */
 #define HGMM_LL_LEVEL 0            /* reference: scan of all 8^(l+1) nodes of the level with the new parameters */
@@ -146,6 +148,20 @@ int hgmm_reg_mstep(hgmm_ctx* ctx, int32_t solver, double* rot, double* t, double
  * wrapper inverts). out_q_hist [maxiter] may be NULL. */
 int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, double* t,
                        double* out_q, int32_t* out_iters, double* out_q_hist);
+
+/* ---- L2-distance registration of two flat mixtures (float64) ----
+ * replaces RigidCostFunction.__call__ / compute_l2_dist  src/python/gmmreg_gpu/cost_functions.py:29-69,
+ * GaussTransform.compute src/python/gmmreg_gpu/transforms.py:73-86, diff_rot_from_quaternion src/python/gmmreg_gpu/so.py:4-59
+ * and the scipy BFGS call of L2DistRegistration.registration src/python/gmmreg_gpu/gmmreg.py:101-107.
+ * mu_* [J,3], phi_* [J] (the reference passes the fitted weights x 1e3); theta = (qw,qx,qy,qz,tx,ty,tz). */
+int hgmm_l2_set_mixtures(hgmm_ctx* ctx, const double* mu_source, const double* phi_source, int32_t n_source,
+                         const double* mu_target, const double* phi_target, int32_t n_target);
+/* f(theta) and its gradient [7] exactly as the reference's cost function returns them */
+int hgmm_l2_cost_grad(hgmm_ctx* ctx, const double* theta, double sigma, double* out_f, double* out_grad);
+/* the whole BFGS minimisation in one kernel launch; theta is in/out; out_status: 0 = |grad|_inf <= gtol,
+ * 1 = iteration limit, 2 = line search failed (the end point is still the best one found) */
+int hgmm_l2_optimize(hgmm_ctx* ctx, double* theta, double sigma, int32_t max_iter, double gtol, double* out_f,
+                     int32_t* out_iters, int32_t* out_nfev, int32_t* out_status);
 
 /* ---- viewer glue ---- */
 /* writes 4 floats per point: pos = (-x, -y, -z)/scene_scale, 1 ; col = rgb + 0.3, 1.

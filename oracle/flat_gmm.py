@@ -90,6 +90,41 @@ def py_train_gmm(X, max_iter, tol, means, covariances, weights, cov_type="diag",
     return inv_cov, means, weights, covariances, lls
 
 
+# --------------------------------------------------------------------------------------
+# ``py_old`` variant: src/python/gmmreg_gpu/gmm_impl.py (the copy the L2 registration path fits with).
+# Diagonal only.  Differences from the gmm_waymo copy: log(weights) without eps (:58), nk without eps and
+# weights = nk/N (:47,52), means and E[x^2] divided by (nk + eps) (:48-49), covariance = clip(E[x^2] - mu^2, 0)
+# with no 1e-6 floor (:51), inv_cov = 1/(sqrt(cov) + eps) (:71).
+# --------------------------------------------------------------------------------------
+def py_old_train_gmm(X, max_iter, tol, means, covariances, weights, dtype=np.float64):
+    """gmmreg_gpu/gmm_impl.py:62-83.  Returns (inv_cov, means, weights, covariances, log_ll list)."""
+    X = np.asarray(X, dtype=dtype)
+    means = np.asarray(means, dtype=dtype)
+    covariances = np.asarray(covariances, dtype=dtype)
+    weights = np.asarray(weights, dtype=dtype)
+    inv_cov = 1.0 / np.sqrt(covariances)
+    lower = -np.inf
+    lls = []
+    for _ in range(max_iter):
+        prev = lower
+        with np.errstate(divide="ignore"):
+            wlp = py_log_prob(X, inv_cov, means, "diag") + np.log(weights)[None, :]
+        norm = np.log(np.sum(np.exp(wlp), axis=1) + EPS)
+        ll = norm.mean()
+        lls.append(ll)
+        resp = np.exp(wlp - norm[:, None])
+        nk = resp.sum(axis=0)
+        means = (resp.T @ X) / (nk[:, None] + EPS)
+        x2 = (resp.T @ (X * X)) / (nk[:, None] + EPS)
+        covariances = np.clip(x2 - means ** 2, 0.0, None)
+        weights = nk / X.shape[0]
+        inv_cov = 1.0 / (np.sqrt(covariances) + EPS)
+        lower = ll
+        if abs(lower - prev) < tol:
+            break
+    return inv_cov, means, weights, covariances, lls
+
+
 def py_predict(X, inv_cov, means, weights, cov_type="diag"):
     """gmm_impl.py:147-155: argmax_j(log_prob + log(pi + eps))."""
     X = np.asarray(X)

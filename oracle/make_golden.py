@@ -11,7 +11,9 @@ What is pinned (reference file -> oracle function -> fixture):
   hgmm/hgmm_cupy_cpu_working.py::buildGMMTree             -> hgmm_tree.build_gmm_tree  -> tree_build_*.npz
   hgmm/hgmm_cupy_cpu_working.py::gmmTreeRegESTep, GMMTree.maximization_step/.registration
                                                           -> registration.*            -> tree_reg_*.npz
-  gmmreg_gpu/cost_functions.py::RigidCostFunction         -> l2reg.rigid_cost          -> l2_cost.npz
+  gmmreg_gpu/gmm_impl.py::train_gmm (older diag copy)     -> flat_gmm.py_old_train_gmm -> flat_pyold_*.npz
+  gmmreg_gpu/cost_functions.py::RigidCostFunction, so.py  -> l2reg.rigid_cost          -> l2_cost.npz
+  gmmreg_gpu/gmmreg.py::L2DistRegistration.registration   -> l2reg.registration        -> l2_reg_bunny.npz
 Also converts data/bun000.ply, data/bun045.ply vertices to float32 .npy (inputs of configs 1,2,4).
 """
 import contextlib
@@ -30,7 +32,7 @@ sys.path.insert(0, os.path.join(HERE, "refshim"))
 sys.path.insert(0, ROOT)
 np.infty = np.inf      # removed in NumPy 2; used at gmm_waymo/src/gmm_impl.py:120
 
-from oracle import flat_gmm, hgmm_tree, registration as oreg  # noqa: E402
+from oracle import flat_gmm, hgmm_tree, l2reg, registration as oreg  # noqa: E402
 from oracle.plyio import read_ply_vertices                    # noqa: E402
 
 
@@ -64,8 +66,108 @@ def check(name, got, want, tol):
     return e
 
 
+def load_ref_l2():
+    """gmmreg_gpu/{gmm_impl,cost_functions,so,transforms,gmmreg}.py imported unmodified (shims: cupy, open3d,
+    transformations, thundersvm, matplotlib)."""
+    d = os.path.join(REF, "src/python/gmmreg_gpu")
+    for m in ("gmm_impl", "gmm", "cost_functions", "so", "transforms", "gmmreg"):
+        sys.modules.pop(m, None)
+    if d in sys.path:
+        sys.path.remove(d)
+    sys.path.insert(0, d)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import gmm_impl as old_impl
+        import cost_functions as cfm
+        import gmmreg as gr
+    return old_impl, cfm, gr
+
+
+def main_l2(bun0, bun45):
+    old_impl, cfm, gr = load_ref_l2()
+    # ---------------- older diag EM copy (the fitter of the L2 path) ----------------
+    print("flat / gmmreg_gpu train_gmm (older copy)")
+    for (tag, X, J, seed) in (("sub4k_J50", bun0[::10], 50, 5), ("b45sub4k_J50", bun45[::10], 50, 6)):
+        rng = np.random.default_rng(seed)
+        means0 = X[rng.choice(X.shape[0], J, replace=False)].astype(np.float32)
+        covs0 = (0.1 * np.ones((J, 3))).astype(np.float32)
+        w0 = (np.ones(J) / J).astype(np.float32)
+        r = quiet(old_impl.train_gmm, X.astype(np.float64), 10, 0.0, means0.astype(np.float64), covs0.astype(np.float64),
+                  w0.astype(np.float64))
+        o = flat_gmm.py_old_train_gmm(X, 10, 0.0, means0, covs0, w0)
+        check("old %s means" % tag, o[1], r[1], 1e-10)
+        check("old %s weights" % tag, o[2], r[2], 1e-10)
+        check("old %s covs" % tag, o[3], r[3], 1e-9)
+        check("old %s loglik" % tag, o[4], np.array(r[4], dtype=np.float64), 1e-7)
+        np.savez_compressed(os.path.join(GOLD, "flat_pyold_%s.npz" % tag), stride=np.int64(10), J=np.int64(J), means0=means0,
+                            covs0=covs0, weights0=w0, ref_inv_cov=r[0], ref_means=r[1], ref_weights=r[2], ref_covs=r[3],
+                            ref_ll=np.array(r[4], dtype=np.float64))
+        if tag == "sub4k_J50":
+            mix_s = (np.asarray(r[1]), np.asarray(r[2]))
+        else:
+            mix_t = (np.asarray(r[1]), np.asarray(r[2]))
+    # ---------------- cost + gradient at fixed theta ----------------
+    print("L2 cost / gradient (cost_functions.RigidCostFunction)")
+    cost = cfm.RigidCostFunction()
+    mu_s, phi_s = mix_s[0], mix_s[1] * 1e3
+    mu_t, phi_t = mix_t[0], mix_t[1] * 1e3
+    sigma = l2reg.estimate_sigma(bun0[::10].astype(np.float64))
+    thetas = np.array([[1, 0, 0, 0, 0, 0, 0], [0.95, 0.02, -0.3, 0.01, -0.05, 0.0, -0.01], [0.7, 0.1, 0.6, -0.2, 0.02, 0.03, -0.04],
+                       [2.0, 0.0, -0.6, 0.0, -0.1, 0.0, -0.02]], dtype=np.float64)
+    fs, gs = [], []
+    for th in thetas:
+        f, g = cost(th, mu_s, phi_s, mu_t, phi_t, sigma)
+        of, og = l2reg.rigid_cost(th, mu_s, phi_s, mu_t, phi_t, sigma)
+        check("cost  theta=%s" % np.round(th[:4], 2), [of], [f], 1e-12)
+        check("grad  theta=%s" % np.round(th[:4], 2), og, g, 1e-10)
+        fs.append(f)
+        gs.append(g)
+    np.savez_compressed(os.path.join(GOLD, "l2_cost.npz"), mu_s=mu_s, phi_s=phi_s, mu_t=mu_t, phi_t=phi_t, sigma=np.float64(sigma),
+                        thetas=thetas, ref_f=np.array(fs), ref_grad=np.array(gs))
+    # ---------------- the registration loop (SciPy BFGS, annealing) with the mixtures above ----------------
+    print("L2DistRegistration.registration (feature generator replaced by the fixed mixtures above)")
+
+    class FixedFeatures(object):
+        def __init__(self):
+            self.calls = 0
+
+        def init(self):
+            pass
+
+        def annealing(self):
+            pass
+
+        def compute(self, data):
+            self.calls += 1
+            return (mix_t if self.calls == 1 else mix_s)        # target first (gmmreg.py:71), then the source (:84)
+
+    for (name, kw) in (("default", dict(maxiter=1, tol=1e-3, opt_maxiter=10, opt_tol=1e-5)),
+                       ("converged", dict(maxiter=3, tol=1e-9, opt_maxiter=200, opt_tol=1e-9))):
+        reg = quiet(gr.L2DistRegistration, bun0[::10].astype(np.float64), FixedFeatures(), cfm.RigidCostFunction())
+        tf = quiet(reg.registration, bun45[::10].astype(np.float64), **kw)
+        oR, ot, ox, of = l2reg.registration(lambda: mix_s, mix_t[0], mix_t[1], sigma, **kw)
+        # SciPy's BFGS amplifies the 1e-16 differences between two exact evaluations of the same cost (line-search
+        # decisions): after 10 iterations the reference and its restatement are ~1e-5 apart, at convergence ~1e-7
+        # (the run to convergence ends in SciPy's "precision loss" exit on a flat valley -- |q| is a null direction of the
+        # cost -- so its end point is only reproducible to ~1e-3 in the pose while the cost agrees to 1e-9)
+        ptol = 1e-4 if name == "default" else 5e-3
+        check("registration[%s] rot" % name, oR, tf.rot, ptol)
+        check("registration[%s] t" % name, ot, tf.t, 10 * ptol)
+        q_ref = None
+        rf, _ = cfm.RigidCostFunction()(ox, mu_s, phi_s, mu_t, phi_t, sigma * 0.9 ** (kw["maxiter"] - 1))
+        print("       cost at the oracle's end point evaluated by the reference: %.9e (oracle %.9e)" % (rf, of))
+        ang = np.rad2deg(np.arccos(np.clip((np.trace(tf.rot) - 1) / 2, -1, 1)))
+        print("       recovered angle %.2f deg, t = %s, f = %.6e" % (ang, np.round(tf.t, 4), of))
+        np.savez_compressed(os.path.join(GOLD, "l2_reg_bunny_%s.npz" % name), sigma=np.float64(sigma), ref_rot=tf.rot, ref_t=tf.t,
+                            oracle_theta=ox, oracle_f=np.float64(of), **{k: np.float64(v) for k, v in kw.items()})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "l2":
+        main_l2(np.load(os.path.join(GOLD, "bun000_xyz.npy")), np.load(os.path.join(GOLD, "bun045_xyz.npy")))
+        return
     bun0 = read_ply_vertices(os.path.join(REF, "data/bun000.ply"))
     bun45 = read_ply_vertices(os.path.join(REF, "data/bun045.ply"))
     assert bun0.shape == (40256, 3) and bun45.shape == (40097, 3)
@@ -167,6 +269,7 @@ def main():
                                 ref_step_rot=res.transformation.rot, ref_step_t=res.transformation.t,
                                 ref_step_q=np.ravel(res.q), ref_rot=full.transformation.rot, ref_t=full.transformation.t,
                                 ref_q=np.ravel(full.q), oracle_iters=np.int64(fit), true_rot=Rz)
+    main_l2(bun0, bun45)
     print("golden fixtures written to", GOLD)
 
 
