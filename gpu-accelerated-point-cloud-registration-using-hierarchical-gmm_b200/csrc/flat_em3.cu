@@ -582,6 +582,14 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
     }
     // shared-memory staged chunks (flat_em5.cu), one CTA per SM: measured faster than the per-batch-barrier kernels from
     // 9 pair columns up (J > 512: 58.9 vs 67.6 us at J = 800, 49.9 vs 55.1 at J = 640; 37.2 vs 33.0 at J = 320)
+    // the same with a barrier-free chunk pipeline (flat_em7.cu)
+    if (one_cta_per_sm == 8 && sdiv >= 5 && sdiv <= 16) {
+        int ctas = num_sms;
+        if ((long long)ctas * 16 > n) ctas = (n + 15) / 16;
+        if (ctas < 1) ctas = 1;
+        *W = sdiv; *Sdiv = sdiv; *G = 1; *grid = ctas; *big = 7;
+        return;
+    }
     if ((one_cta_per_sm == 6 && sdiv >= 5 && sdiv <= 16) || (one_cta_per_sm == 0 && sdiv >= 9 && sdiv <= 15)) {
         int ctas = num_sms;
         if ((long long)ctas * 16 > n) ctas = (n + 15) / 16;
@@ -613,6 +621,7 @@ cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int 
                             cudaStream_t s) {
     const float eps_on = m.flavor != HGMM_FLAVOR_CPP ? 1.f : 0.f;
     const int ncref = m.Jp / 32;
+    if (big == 7) return launch_em_flat7(x, y, z, n, m, cref_blocks, W, grid, partial, rowaux, done_flag, s);
     if (big == 6) return launch_em_flat6(x, y, z, n, m, cref_blocks, grid, partial, rowaux, done_flag, s);
     if (big == 5) return launch_em_flat5(x, y, z, n, m, cref_blocks, W, grid, partial, rowaux, done_flag, s);
     if (big == 4)

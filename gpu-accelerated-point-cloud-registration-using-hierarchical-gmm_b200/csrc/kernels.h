@@ -77,6 +77,10 @@ cudaError_t launch_ffma2_peak(float* out, int blocks, int iters, cudaStream_t s)
 cudaError_t launch_em_flat5(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
                             int W, int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s);
 
+// flat_em7.cu (flat_em5's arithmetic, chunks double-buffered, mbarrier arrive/wait instead of CTA barriers)
+cudaError_t launch_em_flat7(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
+                            int P, int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s);
+
 // flat_em6.cu (one component per thread, densities staged in shared memory)
 cudaError_t launch_em_flat6(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
                             int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s);

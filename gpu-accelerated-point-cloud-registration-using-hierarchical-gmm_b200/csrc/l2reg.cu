@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(kL2Threads) l2_bfgs_kernel(L2Mix mx, double* _
     for (int k = 0; k < 7; ++k) x[k] = theta[k];
     l2_eval(mx, x, sigma, s_red, f, g);
     int nfev = 1, iters = 0, status = 1;
+    bool fresh = true;                                  // H is the identity
     if (tid < 49) H[tid / 7][tid % 7] = (tid / 7 == tid % 7) ? 1.0 : 0.0;
     __syncthreads();
     double gn2 = 0.0;
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(kL2Threads) l2_bfgs_kernel(L2Mix mx, double* _
             dphi0 = 0.0;
 #pragma unroll
             for (int a = 0; a < 7; ++a) { p[a] = -g[a]; dphi0 -= g[a] * g[a]; }
+            fresh = true;
         }
         double a1 = fmin(1.0, 1.01 * 2.0 * (f - f_old) / dphi0);
         if (!(a1 > 0.0)) a1 = 1.0;
@@ -256,7 +258,32 @@ __global__ void __launch_bounds__(kL2Threads) l2_bfgs_kernel(L2Mix mx, double* _
                 if (fabs(a_hi - a_lo) < 1e-16 * fmax(1.0, fabs(a_lo))) break;
             }
         }
-        if (!accepted) { status = 2; break; }
+        if (!accepted) {
+            // The reference's gradient is not the cost's derivative (so.py's diagonal entries, the halved translation part:
+            // cost_functions.py:39), so the Wolfe conditions can be unsatisfiable along p.  Keep the best Armijo point the
+            // search found; failing that, retry once from steepest descent; only then give up (SciPy's status 2).
+            if (a_lo > 0.0 && phi_lo < f) {
+                double xt[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) xt[k] = x[k] + a_lo * p[k];
+                l2_eval(mx, xt, sigma, s_red, f_acc, g_acc);
+                ++nfev;
+                a_acc = a_lo;
+            } else if (!fresh) {
+                __syncthreads();
+                if (tid < 49) H[tid / 7][tid % 7] = (tid / 7 == tid % 7) ? 1.0 : 0.0;
+                __syncthreads();
+                fresh = true;
+                gn2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) gn2 += g[k] * g[k];
+                f_old = f + sqrt(gn2) / 2.0;
+                continue;
+            } else {
+                status = 2;
+                break;
+            }
+        }
         // ---- BFGS update of the inverse Hessian: H' = H - rho (s (Hy)^T + (Hy) s^T) + (rho^2 y^T H y + rho) s s^T
         double s[7], y[7], ys = 0.0;
 #pragma unroll
@@ -287,6 +314,7 @@ __global__ void __launch_bounds__(kL2Threads) l2_bfgs_kernel(L2Mix mx, double* _
             H[a][b] = H[a][b] - rho * (sa * hb + ha * sb) + (rho * rho * yHy + rho) * sa * sb;
         }
         __syncthreads();
+        fresh = false;
         f_old = f;
         f = f_acc;
 #pragma unroll

@@ -8,10 +8,12 @@ out = {}
 eng = hgmm_b200.Engine(0)
 eng.set_points(torch.from_numpy(X).cuda())
 for J in (800, 1024, 640, 320):
+    if len(sys.argv) > 1 and J != int(sys.argv[1]):
+        continue
     rng = np.random.default_rng(1)
     mu0 = X[rng.choice(len(X), J, replace=False)]
     cov0 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J, 1, 1)); w0 = np.full(J, 1 / J, np.float32)
-    for name, variant, tile in (("v3_big_pb8", 0, 1), ("v5_staged", 0, 6), ("v6_staged_scalar", 0, 7)):
+    for name, variant, tile in (("v3_big_pb8", 0, 1), ("v5_staged", 0, 6), ("v7_pipelined", 0, 8)):
         eng.set_profiling(False)
         for _ in range(3):
             eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False, variant=variant, tile_points=tile)
