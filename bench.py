@@ -261,11 +261,11 @@ def main():
     hbm_peak, hbm_src = measured_peaks()
     peak_imm, peak_reg, peak_packed = eng.measure_fp32_peak()
     fp32_peak = peak_packed
-    roof = {"bound": "hbm", "kernel": "em_flat5_kernel", "achieved": bytes_alg / k_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "em_flat7_kernel", "achieved": bytes_alg / k_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": bytes_alg / k_avg_s / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
             "avg_launch_us": k_avg_s * 1e6,
             "note": "J=800 makes this sweep FP32-issue bound (52*J/12 = 3467 flop/B >> the ~10 flop/B ridge); see roofline_fp32"}
-    roof32 = {"bound": "fp32", "kernel": "em_flat5_kernel", "achieved": flops_alg / k_avg_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+    roof32 = {"bound": "fp32", "kernel": "em_flat7_kernel", "achieved": flops_alg / k_avg_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
               "frac": flops_alg / k_avg_s / 1e12 / fp32_peak if fp32_peak > 0 else None,
               "peak_source": "measured live: packed FFMA2 register loop (hgmm_measure_fp32_peak); scalar 3-register FFMA measures "
                              "%.1f, immediate-operand FFMA %.1f TFLOP/s on the same device" % (peak_reg, peak_imm)}

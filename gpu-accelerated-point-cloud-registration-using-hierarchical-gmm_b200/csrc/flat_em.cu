@@ -402,7 +402,11 @@ __global__ void __launch_bounds__(512) flat_reduce_finalize_kernel(FlatModel m, 
                                                                    const double* __restrict__ rowaux, int rows,
                                                                    int* __restrict__ ctrl, int* __restrict__ done_at, int it,
                                                                    double* __restrict__ ll_hist, double n_total) {
-    const bool done = done_at[it] != 0;
+    // programmatic dependent launch: wait for the sweep (and, transitively, everything before it), then let the next
+    // iteration's sweep start its parameter-independent prologue while this kernel runs
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const bool done = __ldcg(done_at + it) != 0;
     if (done) {
         if (blockIdx.x == 0 && threadIdx.x == 0) done_at[it + 1] = 1;
         return;
@@ -419,14 +423,14 @@ __global__ void __launch_bounds__(512) flat_reduce_finalize_kernel(FlatModel m, 
         for (int r = w; r < rows; r += 16) {
             const float* src = partial + (size_t)r * stride + j;
 #pragma unroll
-            for (int k = 0; k < kMom; ++k) v[k] += (double)src[(size_t)k * m.Jp];
+            for (int k = 0; k < kMom; ++k) v[k] += (double)__ldcg(src + (size_t)k * m.Jp);
         }
 #pragma unroll
         for (int k = 0; k < kMom; ++k) sm[w][k][lane] = v[k];
         double l = 0.0, c = 0.0;                 // every warp also folds a slice of the per-row log-lik / live counts
         for (int q = w * 32 + lane; q < rows; q += 512) {
-            l += rowaux[2 * q];
-            c += rowaux[2 * q + 1];
+            l += __ldcg(rowaux + 2 * q);
+            c += __ldcg(rowaux + 2 * q + 1);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -600,7 +604,16 @@ void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s) {
 }
 void launch_flat_reduce_finalize(const FlatModel& m, const float* partial, const double* rowaux, int rows, int* ctrl, int* done_at,
                                  int it, double* ll_hist, double n_total, cudaStream_t s) {
-    flat_reduce_finalize_kernel<<<m.Jp / 32, 512, 0, s>>>(m, partial, rowaux, rows, ctrl, done_at, it, ll_hist, n_total);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(m.Jp / 32);
+    cfg.blockDim = dim3(512);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, flat_reduce_finalize_kernel, m, partial, rowaux, rows, ctrl, done_at, it, ll_hist, n_total);
 }
 
 void launch_flat_finalize(const FlatModel& m, const double* acc, int* ctrl, int* done_at, int it, double* ll_hist, double n_total,

@@ -580,17 +580,18 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
         *W = S; *Sdiv = S; *G = 1; *grid = ctas; *big = 6;
         return;
     }
-    // shared-memory staged chunks (flat_em5.cu), one CTA per SM: measured faster than the per-batch-barrier kernels from
-    // 9 pair columns up (J > 512: 58.9 vs 67.6 us at J = 800, 49.9 vs 55.1 at J = 640; 37.2 vs 33.0 at J = 320)
-    // the same with a barrier-free chunk pipeline (flat_em7.cu)
-    if (one_cta_per_sm == 8 && sdiv >= 5 && sdiv <= 16) {
+    // shared-memory staged chunks with two CTA barriers per chunk (flat_em5.cu), kept selectable for A/B
+    // shared-memory staged chunks with a barrier-free chunk pipeline (flat_em7.cu), one CTA per SM: the default from 9
+    // pair columns up (J > 512; 10-iteration fit of configs[1]: 0.582 ms vs 0.637 for flat_em5, 0.700 for the per-batch
+    // barrier kernel; J = 1024: 0.635 / 0.721 / 0.719; J = 640: 0.498 / 0.535 / 0.580 -- profiles/r01_flat_kernel_variants.json)
+    if ((one_cta_per_sm == 8 && sdiv >= 5 && sdiv <= 16) || (one_cta_per_sm == 0 && sdiv >= 9 && sdiv <= 16)) {
         int ctas = num_sms;
         if ((long long)ctas * 16 > n) ctas = (n + 15) / 16;
         if (ctas < 1) ctas = 1;
         *W = sdiv; *Sdiv = sdiv; *G = 1; *grid = ctas; *big = 7;
         return;
     }
-    if ((one_cta_per_sm == 6 && sdiv >= 5 && sdiv <= 16) || (one_cta_per_sm == 0 && sdiv >= 9 && sdiv <= 15)) {
+    if (one_cta_per_sm == 6 && sdiv >= 5 && sdiv <= 16) {
         int ctas = num_sms;
         if ((long long)ctas * 16 > n) ctas = (n + 15) / 16;
         if (ctas < 1) ctas = 1;

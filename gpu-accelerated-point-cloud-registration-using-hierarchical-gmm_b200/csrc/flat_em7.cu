@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(512, 1) em_flat7_kernel(const float* __restric
                                                           const float* __restrict__ cref_blocks, int n_cref, int Jp, int CH,
                                                           int SB, float* __restrict__ partial, double* __restrict__ rowaux,
                                                           const int* __restrict__ done_flag, float norm_eps_on) {
-    if (*done_flag) return;
     constexpr int PB = 8;
     constexpr int C = P * 32;                                              // e columns
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -79,6 +78,23 @@ __global__ void __launch_bounds__(512, 1) em_flat7_kernel(const float* __restric
         mbar_init(&bars[1], W);
         mbar_fence_init();
     }
+    const int per = (int)(((long long)n + gridDim.x - 1) / gridDim.x);
+    const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
+    // points of staging block sb0 -> (x,x,y,y) (z,z,0,0), plus one batch of padding (copies of the last point)
+    auto stage = [&](int sb0, int cn) {
+        for (int i = tid; i < cn + PB; i += T) {
+            const int src = sb0 + min(i, cn - 1);
+            const float x = px[src], y = py[src], z = pz[src];
+            spts[2 * i] = make_float4(x, x, y, y);
+            spts[2 * i + 1] = make_float4(z, z, 0.f, 0.f);
+        }
+    };
+    // The cloud never changes between EM iterations, so the first block is staged BEFORE the programmatic-dependent-launch
+    // wait: this part of the prologue overlaps the tail of the previous iteration's reduce + finalize kernel.  Everything
+    // that kernel writes (done flag, Cref, packed parameters) is read after the wait.
+    if (hi > lo) stage(lo, min(SB, hi - lo));
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (__ldcg(done_flag)) return;                        // L2 loads for everything the previous kernel wrote
 
     // ---- which pair column, and which share of every chunk's batches, this warp sweeps (as em_flat5_kernel)
     const int full = P == W ? P : (P & ~3);               // columns swept whole by one warp
@@ -90,7 +106,7 @@ __global__ void __launch_bounds__(512, 1) em_flat7_kernel(const float* __restric
         sidx = (warp - full) % nsplit;
     }
 
-    float cref = lane < n_cref ? __ldg(cref_blocks + lane) : -INFINITY;
+    float cref = lane < n_cref ? __ldcg(cref_blocks + lane) : -INFINITY;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cref = fmaxf(cref, __shfl_xor_sync(0xffffffffu, cref, o));
     if (!(cref > kNegBig)) cref = 0.f;
@@ -101,8 +117,8 @@ __global__ void __launch_bounds__(512, 1) em_flat7_kernel(const float* __restric
     {
         const float4* a4 = reinterpret_cast<const float4*>(packed + (live0 ? col * 32 + lane : 0));
         const float4* b4 = reinterpret_cast<const float4*>(packed + (live1 ? (col + P) * 32 + lane : 0));
-        const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), a2 = __ldg(a4 + 2);
-        const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1), b2 = __ldg(b4 + 2);
+        const float4 a0 = __ldcg(a4), a1 = __ldcg(a4 + 1), a2 = __ldcg(a4 + 2);
+        const float4 b0 = __ldcg(b4), b1 = __ldcg(b4 + 1), b2 = __ldcg(b4 + 2);
         k.nmx = make_float2(-a0.x, -b0.x);
         k.nmy = make_float2(-a0.y, -b0.y);
         k.nmz = make_float2(-a0.z, -b0.z);
@@ -119,8 +135,6 @@ __global__ void __launch_bounds__(512, 1) em_flat7_kernel(const float* __restric
     for (int m = 0; m < kMom; ++m) a[m] = make_float2(0.f, 0.f);
     double ll = 0.0, nlive = 0.0;                         // warp 0, lane = point of the chunk
 
-    const int per = (int)(((long long)n + gridDim.x - 1) / gridDim.x);
-    const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
     float2* const ecol = ebuf + col * 32 + lane;          // element p of buffer b's column: ecol[(b * CH + p) * C]
     float* const redcol = red + col * kRedPts;            // this column's partial sums: redcol[b * 16 * 32 + p]
     unsigned g = 0;                                       // chunks done so far: buffer g & 1, mbarrier parity (g >> 1) & 1
@@ -154,14 +168,11 @@ __global__ void __launch_bounds__(512, 1) em_flat7_kernel(const float* __restric
 
     for (int sb0 = lo; sb0 < hi; sb0 += SB) {
         const int cn = min(SB, hi - sb0);
-        __syncthreads();                                  // the previous block's points are no longer read; barriers initialised
-        for (int i = tid; i < cn + PB; i += T) {          // one batch of padding: copies of the last point
-            const int src = sb0 + min(i, cn - 1);
-            const float x = px[src], y = py[src], z = pz[src];
-            spts[2 * i] = make_float4(x, x, y, y);
-            spts[2 * i + 1] = make_float4(z, z, 0.f, 0.f);
+        if (sb0 != lo) {
+            __syncthreads();                              // the previous block's points are no longer read
+            stage(sb0, cn);
         }
-        __syncthreads();
+        __syncthreads();                                  // points staged (and, the first time, barriers initialised)
         const int K = (cn + CH - 1) / CH;
         pass1(0, min(CH, cn), g & 1);
         __syncwarp();
@@ -300,6 +311,7 @@ __global__ void __launch_bounds__(512, 1) em_flat7_kernel(const float* __restric
             }
         }
     }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the reduce + finalize kernel may start launching
     // ---- warps sharing a column fold their partial moments in a fixed order (the e buffers are free now)
     __syncthreads();
     if (nsplit > 1 && sidx > 0) {
@@ -369,9 +381,20 @@ static cudaError_t launch7(const float* x, const float* y, const float* z, int n
     flat7_shape(P * 32, smem_optin, &CH, &SB);
     const int W = flat5_warps(P);
     const float eps_on = m.flavor != HGMM_FLAVOR_CPP ? 1.f : 0.f;
-    em_flat7_kernel<P><<<grid, W * 32, flat7_smem_bytes(CH, SB, P * 32), s>>>(x, y, z, n, m.packed, cref_blocks, m.Jp / 32, m.Jp, CH, SB,
-                                                                              partial, rowaux, done_flag, eps_on);
-    return cudaGetLastError();
+    // programmatic dependent launch: this grid may start while the previous kernel of the stream is still finishing; the
+    // kernel itself waits (griddepcontrol.wait) before touching anything that kernel produces
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(W * 32);
+    cfg.dynamicSmemBytes = flat7_smem_bytes(CH, SB, P * 32);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, em_flat7_kernel<P>, x, y, z, n, m.packed, cref_blocks, m.Jp / 32, m.Jp, CH, SB, partial, rowaux,
+                              done_flag, eps_on);
 }
 
 cudaError_t launch_em_flat7(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
