@@ -316,7 +316,9 @@ def main():
                "config": {"workload": "configs[1]: flat GMM J=800 full-cov on bun000, 10 EM iterations per step",
                           "points_per_gpu": n, "components": J, "em_iters_per_step": EM_ITERS, "init": "seeded points, Sigma0=1e-4*I",
                           "l2": "256 MiB buffer written between steps (the 10 sweeps inside a step re-read the 483 kB cloud as the algorithm does)",
-                          "parallelism": "dp%d: points sharded, fp64 NCCL all-reduce of J*10 moments per EM iteration" % world},
+                          "parallelism": ("dp%d: points sharded; per EM iteration the J*10 fp64 moments are exchanged " % world) +
+                                         ("inside the M-step kernel by NVLink stores into peer memory (no NCCL call)" if eng.p2p_enabled
+                                          else "by one fp64 ncclAllReduce" if world > 1 else "(single rank: no exchange)")},
                "em_iters_per_sec": EM_ITERS * args.steps / (t_ms * 1e-3),
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": float(te.item()) / args.steps * 1e3, "timing": "wall clock, barrier+synchronize on both sides"},

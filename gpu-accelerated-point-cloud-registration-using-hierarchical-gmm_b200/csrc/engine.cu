@@ -142,6 +142,11 @@ struct hgmm_ctx {
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory exchange window of the flat M-step (xchg.cuh)
+    void* xwin = nullptr;                 // this rank's window (cudaMalloc)
+    void* xpeer[kXchgMaxRanks] = {};      // every rank's window as mapped here (own entry = xwin)
+    bool p2p_ready = false;
+    uint32_t xepoch = 0;
 };
 
 #define CK(call)                                                                                  \
@@ -169,6 +174,16 @@ static int allreduce(hgmm_ctx* ctx, double* buf, size_t count) {
         return HGMM_ERR_NCCL;
     }
     return HGMM_OK;
+}
+
+static void p2p_release(hgmm_ctx* ctx) {
+    for (int r = 0; r < kXchgMaxRanks; ++r) {
+        if (ctx->xpeer[r] && ctx->xpeer[r] != ctx->xwin) cudaIpcCloseMemHandle(ctx->xpeer[r]);
+        ctx->xpeer[r] = nullptr;
+    }
+    if (ctx->xwin) cudaFree(ctx->xwin);
+    ctx->xwin = nullptr;
+    ctx->p2p_ready = false;
 }
 
 static int64_t level_base_h(int l) {
@@ -224,6 +239,7 @@ int hgmm_destroy(hgmm_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    p2p_release(ctx);
     DevBuf* all[] = {&ctx->bx, &ctx->by, &ctx->bz, &ctx->stage, &ctx->acc, &ctx->ctrl, &ctx->qstate, &ctx->hist, &ctx->f_means,
                      &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->done_at, &ctx->partial, &ctx->rowaux, &ctx->cref, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
                      &ctx->t_cplx, &ctx->t_packed, &ctx->t_init, &ctx->p_group, &ctx->p_tilecnt, &ctx->p_tileoff, &ctx->p_segbase,
@@ -381,6 +397,17 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
                 CK(launch_em_flat2(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, m.cref_blocks, JT, W, Sdiv,
                                    G, grid, big, ctx->partial.as<float>(), ctx->rowaux.as<double>(), done_at + it, s));
             if (prof) CK(cudaEventRecord(ctx->pev[2 * it + 1], s));
+            if (ctx->nranks > 1 && ctx->p2p_ready && cfg->reserved != 3) {
+                // multi-GPU over peer memory: reduce + NVLink exchange + finalize in one kernel (xchg.cuh)
+                XchgView xv;
+                for (int r = 0; r < kXchgMaxRanks; ++r) xv.data[r] = reinterpret_cast<uint4*>(ctx->xpeer[r]);
+                xv.rank = ctx->rank; xv.nranks = ctx->nranks; xv.epoch = ++ctx->xepoch;
+                CK(launch_flat_reduce_exchange_finalize(m, ctx->partial.as<float>(), ctx->rowaux.as<double>(), grid * G,
+                                                        ctx->ctrl.as<int>(), done_at, it, ctx->hist.as<double>(),
+                                                        (double)ctx->n_total, xv, s));
+                ctx->launches += 2;
+                continue;
+            }
             if (ctx->nranks <= 1 && cfg->reserved != 3) {      // single GPU: reduce + finalize in one kernel
                 launch_flat_reduce_finalize(m, ctx->partial.as<float>(), ctx->rowaux.as<double>(), grid * G, ctx->ctrl.as<int>(),
                                             done_at, it, ctx->hist.as<double>(), (double)ctx->n_total, s);
@@ -410,6 +437,7 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
         CK(cudaMemcpyAsync(out_ll, ctx->hist.p, (size_t)cfg->max_iter * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (out_iters) *out_iters = ctx->h_ctrl[1];
+    if (ctx->h_ctrl[7]) FAIL(HGMM_ERR_NCCL, "peer-memory exchange timed out: a rank is missing or the ranks' call sequences differ");
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_ms[0] = ms; ctx->last_ms[1] = 0; ctx->last_ms[2] = 0;
@@ -900,12 +928,70 @@ int hgmm_comm_init(hgmm_ctx* ctx, int rank, int nranks, const void* id128) {
     return HGMM_OK;
 }
 
+// ---- peer-memory exchange window (one process per GPU on one box; handles travel over the caller's bootstrap channel)
+int hgmm_p2p_export(hgmm_ctx* ctx, void* out_handle64) {
+    if (!ctx || !out_handle64) return HGMM_ERR_INVALID;
+    if (ctx->nranks < 2) FAIL(HGMM_ERR_STATE, "hgmm_comm_init first");
+    if (ctx->nranks > kXchgMaxRanks) FAIL(HGMM_ERR_INVALID, "peer-memory exchange supports at most 8 ranks");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->xwin) {
+        CK(cudaMalloc(&ctx->xwin, kXchgBytes));
+        CK(cudaMemset(ctx->xwin, 0, kXchgBytes));
+        CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->xwin));
+    memcpy(out_handle64, &h, 64);
+    return HGMM_OK;
+}
+
+int hgmm_p2p_attach(hgmm_ctx* ctx, const void* handles, int32_t n_handles) {
+    if (!ctx || !handles) return HGMM_ERR_INVALID;
+    if (!ctx->xwin) FAIL(HGMM_ERR_STATE, "hgmm_p2p_export first");
+    if (n_handles != ctx->nranks) FAIL(HGMM_ERR_INVALID, "one handle per rank, in rank order");
+    CK(cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->nranks; ++r) {
+        if (r == ctx->rank) {
+            ctx->xpeer[r] = ctx->xwin;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; ++q)
+                if (ctx->xpeer[q] && ctx->xpeer[q] != ctx->xwin) { cudaIpcCloseMemHandle(ctx->xpeer[q]); ctx->xpeer[q] = nullptr; }
+            ctx->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e) + " (no peer access between these devices?)";
+            return HGMM_ERR_CUDA;
+        }
+        ctx->xpeer[r] = p;
+    }
+    ctx->xepoch = 0;
+    ctx->p2p_ready = true;
+    return HGMM_OK;
+}
+
+int hgmm_p2p_detach(hgmm_ctx* ctx) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    p2p_release(ctx);
+    return HGMM_OK;
+}
+
+int hgmm_p2p_enabled(const hgmm_ctx* ctx) { return ctx && ctx->p2p_ready ? 1 : 0; }
+
 int hgmm_comm_destroy(hgmm_ctx* ctx) {
     if (!ctx) return HGMM_ERR_INVALID;
     if (ctx->comm && g_nccl.CommDestroy) {
         cudaStreamSynchronize(ctx->stream);
         g_nccl.CommDestroy(ctx->comm);
     }
+    cudaStreamSynchronize(ctx->stream);
+    p2p_release(ctx);
     ctx->comm = nullptr;
     ctx->nranks = 1;
     ctx->rank = 0;

@@ -466,6 +466,8 @@ __global__ void __launch_bounds__(512) flat_reduce_finalize_kernel(FlatModel m, 
     }
 }
 
+#include "xchg.cuh"
+
 // ------------------------------------------------------------------------------------------
 // hard assignment / level log-likelihood scan (phase A only, components streamed through smem)
 // ------------------------------------------------------------------------------------------

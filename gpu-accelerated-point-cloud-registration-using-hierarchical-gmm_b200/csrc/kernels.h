@@ -22,6 +22,19 @@ struct FlatModel {
     float* cref_blocks;        // [Jp/32] max c2 of each 32-component slot (the sweep's fixed reference is their maximum)
 };
 
+// ---- multi-GPU exchange window of the flat M-step (xchg.cuh): every rank maps every peer's window
+constexpr int kXchgMaxRanks = 8;
+constexpr int kXchgMaxCtas = 32;                 // Jp / 32 <= 32
+constexpr int kXchgMaxJ = 1024;
+constexpr int kXchgHdr = 2 * kXchgMaxCtas;       // doubles: per-CTA (sum log-lik, live points)
+constexpr size_t kXchgCells = (size_t)2 * kXchgMaxRanks * (kXchgHdr + (size_t)kMom * kXchgMaxJ);
+constexpr size_t kXchgBytes = kXchgCells * 16;   // one fp64 value per 16-byte self-validating cell (xchg.cuh)
+struct XchgView {
+    uint4* data[kXchgMaxRanks];                  // window of rank r (own window: the local pointer)
+    int rank, nranks;
+    uint32_t epoch;                              // same on every rank; parity selects the half of the window
+};
+
 struct TreeModel {
     int L;                     // levels
     int nt;                    // total nodes 8(8^L-1)/7
@@ -56,6 +69,9 @@ void flat2_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* JT, int* W,
 cudaError_t launch_em_flat2(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
                             int JT, int W, int Sdiv, int G, int grid, int big, float* partial, double* rowaux,
                             const int* done_flag, cudaStream_t s);
+cudaError_t launch_flat_reduce_exchange_finalize(const FlatModel& m, const float* partial, const double* rowaux, int rows, int* ctrl,
+                                                 int* done_at, int it, double* ll_hist, double n_total, const XchgView& xc,
+                                                 cudaStream_t s);
 cudaError_t launch_flat_reduce(const float* partial, const double* rowaux, int rows, const FlatModel& m, double* acc,
                                const int* done_flag, cudaStream_t s);
 int flat_pick_tile(int n, int num_sms, int requested);

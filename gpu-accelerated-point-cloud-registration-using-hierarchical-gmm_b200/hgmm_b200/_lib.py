@@ -68,6 +68,10 @@ SIGNATURES = {
     "hgmm_comm_unique_id": (C.c_int, [_VP]),
     "hgmm_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "hgmm_comm_destroy": (C.c_int, [_VP]),
+    "hgmm_p2p_export": (C.c_int, [_VP, _VP]),
+    "hgmm_p2p_attach": (C.c_int, [_VP, _VP, C.c_int32]),
+    "hgmm_p2p_detach": (C.c_int, [_VP]),
+    "hgmm_p2p_enabled": (C.c_int, [_VP]),
     "hgmm_measure_fp32_peak": (C.c_int, [_VP, _VP]),
     "hgmm_last_timing": (C.c_int, [_VP, _VP]),
     "hgmm_set_profiling": (C.c_int, [_VP, C.c_int]),

@@ -42,14 +42,50 @@ def broadcast_bytes(payload, src=0):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def attach_communicator(engine):
-    """create libhgmm's NCCL communicator for every rank of the default process group."""
+def allgather_bytes(payload):
+    """every rank's fixed-length bytes object, in rank order, over the default torch.distributed group (any backend)."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    out = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    return [bytes(t.cpu().numpy().tobytes()) for t in out]
+
+
+def attach_communicator(engine, p2p=None):
+    """create libhgmm's NCCL communicator for every rank of the default process group and, when the ranks are the GPUs
+    of one box (<= 8) that can map each other's memory, the peer-memory exchange windows of the flat fit (NVLink stores
+    fused into the M-step kernel instead of ncclAllReduce).  p2p: True / False / None = on unless HGMM_NO_P2P=1.
+    Every rank must reach the same decision, so a rank that cannot attach makes all of them fall back to NCCL."""
+    import os
+    import torch
     import torch.distributed as dist
     from .engine import Engine
+    from ._lib import HgmmError
     rank, world = dist.get_rank(), dist.get_world_size()
     uid = Engine.comm_unique_id() if rank == 0 else b""
     uid = broadcast_bytes(uid, 0)
     engine.comm_init(rank, world, uid)
+    if p2p is None:
+        p2p = os.environ.get("HGMM_NO_P2P", "0") != "1"
+    if p2p and 2 <= world <= 8:
+        try:
+            handle = engine.p2p_export()
+        except HgmmError:
+            handle = b"\0" * 64
+        handles = allgather_bytes(handle)
+        ok = all(any(h) for h in handles)
+        if ok:
+            try:
+                engine.p2p_attach(handles)
+            except HgmmError:
+                ok = False
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and engine.p2p_enabled:
+            engine.p2p_detach()
     return rank, world
 
 

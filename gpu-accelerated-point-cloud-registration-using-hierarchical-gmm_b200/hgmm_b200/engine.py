@@ -228,6 +228,27 @@ class Engine:
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id_bytes))
         self._check(self._lib.hgmm_comm_init(self._ctx, int(rank), int(nranks), C.cast(buf, C.c_void_p)), "hgmm_comm_init")
 
+    def p2p_export(self):
+        """this rank's exchange-window handle (64 bytes, cudaIpcMemHandle_t)"""
+        buf = (C.c_char * 64)()
+        self._check(self._lib.hgmm_p2p_export(self._ctx, C.cast(buf, C.c_void_p)), "hgmm_p2p_export")
+        return bytes(buf)
+
+    def p2p_attach(self, handles):
+        """handles: one 64-byte handle per rank, in rank order"""
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != 64 * len(handles):
+            raise ValueError("every handle must be 64 bytes")
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.hgmm_p2p_attach(self._ctx, C.cast(buf, C.c_void_p), len(handles)), "hgmm_p2p_attach")
+
+    def p2p_detach(self):
+        self._check(self._lib.hgmm_p2p_detach(self._ctx), "hgmm_p2p_detach")
+
+    @property
+    def p2p_enabled(self):
+        return bool(self._lib.hgmm_p2p_enabled(self._ctx))
+
     def comm_destroy(self):
         self._check(self._lib.hgmm_comm_destroy(self._ctx), "hgmm_comm_destroy")
 

@@ -175,6 +175,16 @@ int hgmm_fill_vbo(hgmm_ctx* ctx, float* vbo_positions, float* vbo_colors, float 
 int hgmm_comm_unique_id(void* out_id128);
 int hgmm_comm_init(hgmm_ctx* ctx, int rank, int nranks, const void* id128);
 int hgmm_comm_destroy(hgmm_ctx* ctx);
+/* Peer-memory exchange for the flat fit (ranks = GPUs of one box, one process each; after hgmm_comm_init).
+ * hgmm_p2p_export allocates this rank's exchange window and returns its 64-byte cudaIpcMemHandle_t; the caller gathers
+ * the handles of all ranks (any channel) and passes them, in rank order, to hgmm_p2p_attach.  From then on every EM
+ * iteration of hgmm_fit_flat is two kernels: the sweep, and one that folds the rank's partial sums, stores them into
+ * every peer's window over NVLink, adds the ranks' contributions in rank order and finalizes -- no NCCL call, no third
+ * launch.  Without these calls (or if the devices cannot map each other) the NCCL all-reduce path is used. */
+int hgmm_p2p_export(hgmm_ctx* ctx, void* out_handle64);
+int hgmm_p2p_attach(hgmm_ctx* ctx, const void* handles, int32_t n_handles);
+int hgmm_p2p_detach(hgmm_ctx* ctx);                 /* back to the NCCL path (collective decision of the caller) */
+int hgmm_p2p_enabled(const hgmm_ctx* ctx);
 
 /* ---- measurement helper ---- */
 /* FP32 FMA throughput of this device in TFLOP/s, out_tflops[3]: [0] scalar FFMA with immediate

@@ -21,3 +21,8 @@ print("# per-kernel device time from `ncu --metrics gpu__time_duration.sum --clo
 print("# kernel | launches | avg ns | share of captured device time")
 for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("%-78s %5d %11.1f %6.1f%%" % (name, c, t / c, 100 * t / tot))
+own = {k: v for k, v in agg.items() if "peak_kernel" not in k and not k.startswith("void at::") and "aos_to_soa" not in k}
+t2 = sum(a[1] for a in own.values())
+print("# the step's own kernels only (peak probes, torch's L2-flush fill and the one-off upload excluded): share of one EM step")
+for name, (c, t) in sorted(own.items(), key=lambda kv: -kv[1][1]):
+    print("%-78s %5d %11.1f %6.1f%%" % (name, c, t / c, 100 * t / t2))

@@ -38,6 +38,26 @@ def main():
     w0 = np.full(J, 1 / J, np.float32)
     r = eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=6)
     rd = eng.fit_flat(mu0, np.full((J, 3), 2e-4, np.float32), w0, cov_type="diag", max_iter=6)
+    # ---- flat J = 800 (the flat_em7 sweep + the fused reduce / NVLink exchange / finalize kernel), early stop included
+    J8 = 800
+    mu8 = X[np.random.default_rng(3).choice(len(X), J8, replace=False)]
+    cov8 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J8, 1, 1))
+    w8 = np.full(J8, 1 / J8, np.float32)
+    p2p_on = eng.p2p_enabled
+    r8 = eng.fit_flat(mu8, cov8, w8, cov_type="full", max_iter=8)
+    r8b = eng.fit_flat(mu8, cov8, w8, cov_type="full", max_iter=8)
+    rdt = eng.fit_flat(mu8, np.full((J8, 3), 1e-4, np.float32), w8, cov_type="diag", max_iter=40, tol=1e-3)
+    # every rank must hold bit-identical replicas
+    chk = torch.from_numpy(np.concatenate([r8["means"].ravel(), r8["covs"].ravel(), r8["weights"].ravel()]).astype(np.float64)).cuda()
+    lo_, hi_ = chk.clone(), chk.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    replicas_identical = bool((lo_ == hi_).all().item())
+    if p2p_on:
+        eng.p2p_detach()                         # same fits over ncclAllReduce
+        r8n = eng.fit_flat(mu8, cov8, w8, cov_type="full", max_iter=8)
+    else:
+        r8n = r8
     # ---- tree
     L = 3
     init = X[H.reference_init_indices(L)]
@@ -58,7 +78,16 @@ def main():
         tse = ref.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False)
         ref.reg_set_target(T)
         rot1, t1, q1, it1, _ = ref.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+        s8 = ref.fit_flat(mu8, cov8, w8, cov_type="full", max_iter=8)
+        sdt = ref.fit_flat(mu8, np.full((J8, 3), 1e-4, np.float32), w8, cov_type="diag", max_iter=40, tol=1e-3)
+        assert replicas_identical, "ranks hold different replicas"
+        assert np.array_equal(r8["means"], r8b["means"]) and np.array_equal(r8["covs"], r8b["covs"]), "not run-to-run reproducible"
+        assert rdt["iters"] == sdt["iters"] < 40, (rdt["iters"], sdt["iters"])
+        print("P2P", p2p_on, flush=True)
         errs = {
+            "flat800_p2p": max(rel_fro(r8["means"], s8["means"]), rel_fro(r8["covs"], s8["covs"]), rel_fro(r8["weights"], s8["weights"]), rel_fro(r8["ll"], s8["ll"])),
+            "flat800_nccl": max(rel_fro(r8n["means"], s8["means"]), rel_fro(r8n["covs"], s8["covs"]), rel_fro(r8n["weights"], s8["weights"])),
+            "flat800_diag_tol": max(rel_fro(rdt["means"], sdt["means"]), rel_fro(rdt["covs"], sdt["covs"])),
             "flat_full": max(rel_fro(r["means"], s["means"]), rel_fro(r["covs"], s["covs"]), rel_fro(r["weights"], s["weights"]), rel_fro(r["ll"], s["ll"])),
             "flat_diag": max(rel_fro(rd["means"], sd["means"]), rel_fro(rd["covs"], sd["covs"]), rel_fro(rd["weights"], sd["weights"])),
             "tree_level": max(rel_fro(tr["pi"], ts["pi"]), rel_fro(tr["mu"], ts["mu"]), rel_fro(tr["cov"], ts["cov"])),

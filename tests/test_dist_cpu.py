@@ -39,6 +39,9 @@ def _worker(rank, world, port, q):
     payload = bytes(range(128)) if rank == 0 else b""
     got = hd.broadcast_bytes(payload, 0)
     assert got == bytes(range(128))
+    # bootstrap channel used for the 64-byte IPC handles of the peer-memory exchange windows (rank order preserved)
+    hs = hd.allgather_bytes(bytes([rank + 1]) * 64)
+    assert hs == [bytes([r + 1]) * 64 for r in range(world)]
     # one tree E-step: moments are additive over shards -> all-reduce == unsharded
     L = 2
     nt = hgmm_tree.n_total(L)
