@@ -14,7 +14,8 @@
 // "ready" signal (the low-latency protocol NCCL uses for small messages, here fused into the M-step).  8-byte stores are
 // single-copy atomic, the two words of a cell are validated independently.
 // CTA b of every rank owns components [32b, 32b+32): it stores its 32 x 10 sums (+ its copy of the two scalars) into
-// slot `rank` of every PEER window, then polls its OWN window for the peers' CTA b -- a CTA never waits for a CTA that is
+// slot `rank` of every PEER window, then polls its OWN window for the peers' CTA b (warp r collects rank r, the 12 cells of a
+// lane loaded together so the R-1 polls cost one L2 round trip, not 12 (R-1)) -- a CTA never waits for a CTA that is
 // waiting for it, so no co-scheduling is needed.  Every rank adds the contributions in rank order 0..R-1 (its own from
 // registers): replicas stay bit-identical.  A rank is at most one epoch ahead of any other (its next push needs their
 // previous one), hence two parities suffice.
@@ -25,17 +26,37 @@ __device__ __forceinline__ void xchg_put(uint4* cell, double v, uint32_t epoch) 
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<char*>(cell) + 8), "r"((uint32_t)(u >> 32)), "r"(epoch)
                  : "memory");
 }
-// false on timeout
-__device__ __forceinline__ bool xchg_get(const uint4* cell, uint32_t epoch, long long t0, double& v) {
-    uint32_t lo, f0, hi, f1;
+// one peer's contribution for this lane's component: all 12 cells are loaded together (independent loads, ONE L2 round
+// trip when the data has arrived) and re-polled until every word carries the epoch.  false on timeout.
+__device__ __forceinline__ bool xchg_get_row(const uint4* src, size_t Jp, int j, int b, bool hdr_lane, uint32_t epoch, double* v) {
+    const long long t0 = clock64();
     for (;;) {
-        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(f0) : "l"(cell) : "memory");
-        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi), "=r"(f1) : "l"(reinterpret_cast<const char*>(cell) + 8) : "memory");
-        if (f0 == epoch && f1 == epoch) break;
+        uint4 c[kMom + 2];
+#pragma unroll
+        for (int k = 0; k < kMom; ++k) {
+            const uint4* cell = src + kXchgHdr + (size_t)k * Jp + j;
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c[k].x), "=r"(c[k].y), "=r"(c[k].z), "=r"(c[k].w)
+                         : "l"(cell) : "memory");
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint4* cell = src + 2 * b + h;
+            if (hdr_lane)
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c[kMom + h].x), "=r"(c[kMom + h].y),
+                             "=r"(c[kMom + h].z), "=r"(c[kMom + h].w) : "l"(cell) : "memory");
+            else
+                c[kMom + h] = make_uint4(0u, epoch, 0u, epoch);
+        }
+        bool all = true;
+#pragma unroll
+        for (int k = 0; k < kMom + 2; ++k) all = all && c[k].y == epoch && c[k].w == epoch;
+        if (all) {
+#pragma unroll
+            for (int k = 0; k < kMom + 2; ++k) v[k] = __longlong_as_double((long long)(((unsigned long long)c[k].z << 32) | c[k].x));
+            return true;
+        }
         if (clock64() - t0 > 6000000000LL) return false;     // ~3 s: a peer died or the ranks' call sequences diverged
     }
-    v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
-    return true;
 }
 
 __global__ void __launch_bounds__(512) flat_reduce_exchange_finalize_kernel(FlatModel m, const float* __restrict__ partial,
@@ -49,10 +70,14 @@ __global__ void __launch_bounds__(512) flat_reduce_exchange_finalize_kernel(Flat
         if (blockIdx.x == 0 && threadIdx.x == 0) done_at[it + 1] = 1;
         return;
     }
-    __shared__ double sm[16][kMom][33];
+    __shared__ double sm[16][kMom][33];                 // the 16 warps' partial sums; afterwards the peers' rows
     __shared__ double s_aux[16][2];
+    __shared__ int s_bad;
+    static_assert(sizeof(double) * kXchgMaxRanks * (kMom + 2) * 32 <= sizeof(double) * 16 * kMom * 33, "peer rows must fit in sm");
+    double(*xs)[kMom + 2][32] = reinterpret_cast<double(*)[kMom + 2][32]>(&sm[0][0][0]);     // [rank][cell][lane]
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int j = blockIdx.x * 32 + lane;
+    if (tid == 0) s_bad = 0;
     {
         double v[kMom];
 #pragma unroll
@@ -81,70 +106,73 @@ __global__ void __launch_bounds__(512) flat_reduce_exchange_finalize_kernel(Flat
         }
     }
     __syncthreads();
-    if (w != 0) return;
-    double A[kMom];
-#pragma unroll
-    for (int k = 0; k < kMom; ++k) {
-        double t = 0.0;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) t += sm[q][k][lane];
-        A[k] = t;
-    }
-    double ll = 0.0, total = 0.0;
-    for (int q = 0; q < 16; ++q) {
-        ll += s_aux[q][0];
-        total += s_aux[q][1];
-    }
-    // ---------------- exchange
     const int R = xc.nranks, me = xc.rank, b = blockIdx.x;
     const uint32_t epoch = xc.epoch;
     const size_t slot = kXchgHdr + (size_t)kMom * kXchgMaxJ;
-    const size_t my_off = ((size_t)(epoch & 1u) * kXchgMaxRanks + me) * slot;
-    for (int r = 0; r < R; ++r) {                       // push into every peer window: 16-byte cells, 512-byte rows per warp
-        if (r == me) continue;
-        uint4* dst = xc.data[r] + my_off;
-#pragma unroll
-        for (int k = 0; k < kMom; ++k) xchg_put(dst + kXchgHdr + (size_t)k * m.Jp + j, A[k], epoch);
-        if (lane == 0) {
-            xchg_put(dst + 2 * b, ll, epoch);
-            xchg_put(dst + 2 * b + 1, total, epoch);
-        }
-    }
-    // ---------------- add the ranks' contributions in rank order (own from registers, peers' as they arrive)
-    double S[kMom], sll = 0.0, stot = 0.0;
-#pragma unroll
-    for (int k = 0; k < kMom; ++k) S[k] = 0.0;
-    bool ok = true;
-    const long long t0 = clock64();
-    for (int r = 0; r < R; ++r) {
-        if (r == me) {
-#pragma unroll
-            for (int k = 0; k < kMom; ++k) S[k] += A[k];
-            sll += ll;
-            stot += total;
-            continue;
-        }
-        const uint4* src = xc.data[me] + ((size_t)(epoch & 1u) * kXchgMaxRanks + r) * slot;
-        double v = 0.0;
+    const size_t par_off = (size_t)(epoch & 1u) * kXchgMaxRanks * slot;
+    double A[kMom], ll = 0.0, total = 0.0;
+    if (w == 0) {
 #pragma unroll
         for (int k = 0; k < kMom; ++k) {
-            ok = ok && xchg_get(src + kXchgHdr + (size_t)k * m.Jp + j, epoch, t0, v);
-            S[k] += v;
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) t += sm[q][k][lane];
+            A[k] = t;
         }
-        ok = ok && xchg_get(src + 2 * b, epoch, t0, v);
-        sll += v;
-        ok = ok && xchg_get(src + 2 * b + 1, epoch, t0, v);
-        stot += v;
+        for (int q = 0; q < 16; ++q) {
+            ll += s_aux[q][0];
+            total += s_aux[q][1];
+        }
+        // ---------------- push this rank's sums into every peer window: 16-byte cells, 512-byte rows per warp
+        for (int r = 0; r < R; ++r) {
+            if (r == me) continue;
+            uint4* dst = xc.data[r] + par_off + (size_t)me * slot;
+#pragma unroll
+            for (int k = 0; k < kMom; ++k) xchg_put(dst + kXchgHdr + (size_t)k * m.Jp + j, A[k], epoch);
+            if (lane == 0) {
+                xchg_put(dst + 2 * b, ll, epoch);
+                xchg_put(dst + 2 * b + 1, total, epoch);
+            }
+        }
     }
-    ok = __all_sync(0xffffffffu, ok);
-    if (!ok) {
+    __syncthreads();                                    // warp 0 has consumed sm: it now receives the peers' rows
+    // ---------------- warp r collects rank r's contribution from this rank's own window (all peers polled in parallel)
+    if (w < R && w != me) {
+        double v[kMom + 2];
+        const bool ok = xchg_get_row(xc.data[me] + par_off + (size_t)w * slot, (size_t)m.Jp, j, b, lane == 0, epoch, v);
+        if (!ok) s_bad = 1;
+#pragma unroll
+        for (int k = 0; k < kMom + 2; ++k) xs[w][k][lane] = v[k];
+    }
+    __syncthreads();
+    if (w != 0) return;
+    if (s_bad) {
         if (lane == 0) ctrl[7] = 1;
         return;
     }
+    // ---------------- add the ranks' contributions in rank order (own from registers)
+    {
+        double S[kMom], sll = 0.0, stot = 0.0;
 #pragma unroll
-    for (int k = 0; k < kMom; ++k) A[k] = S[k];
-    ll = sll;
-    total = stot;
+        for (int k = 0; k < kMom; ++k) S[k] = 0.0;
+        for (int r = 0; r < R; ++r) {
+            if (r == me) {
+#pragma unroll
+                for (int k = 0; k < kMom; ++k) S[k] += A[k];
+                sll += ll;
+                stot += total;
+            } else {
+#pragma unroll
+                for (int k = 0; k < kMom; ++k) S[k] += xs[r][k][lane];
+                sll += xs[r][kMom][0];
+                stot += xs[r][kMom + 1][0];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kMom; ++k) A[k] = S[k];
+        ll = sll;
+        total = stot;
+    }
     float my_c2 = -INFINITY;
     if (j < m.J) my_c2 = finalize_component(m, j, A, total, n_total);
 #pragma unroll
