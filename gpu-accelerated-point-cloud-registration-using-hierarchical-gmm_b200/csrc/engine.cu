@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -116,6 +117,9 @@ struct hgmm_ctx {
     DevBuf hist;         // doubles (ll / q history)
     int* h_ctrl = nullptr;      // pinned, 8 ints
     double* h_dbl = nullptr;    // pinned, 64 doubles
+    int* h_prog = nullptr;      // pinned + mapped, 4 ints: the tree build's progress words, written by the M-step kernel
+    int* d_prog = nullptr;      // device view of h_prog
+    float* h_params = nullptr;  // pinned, kMaxFlatJ x 13 floats: the flat fit's initial (means | covs | weights) in one copy
 
     // flat model
     FlatModel fm{};
@@ -224,7 +228,11 @@ int hgmm_create(hgmm_ctx** out, int device, void* stream) {
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     if (cudaMallocHost((void**)&ctx->h_ctrl, 8 * sizeof(int)) != cudaSuccess ||
-        cudaMallocHost((void**)&ctx->h_dbl, 64 * sizeof(double)) != cudaSuccess || ctx->ctrl.ensure(8 * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_dbl, 64 * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_params, (size_t)kMaxFlatJ * 13 * sizeof(float)) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->h_prog, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->d_prog, ctx->h_prog, 0) != cudaSuccess ||
+        ctx->ctrl.ensure(8 * sizeof(int)) != cudaSuccess ||
         ctx->qstate.ensure(4 * sizeof(double)) != cudaSuccess || ctx->nchunks.ensure(sizeof(int)) != cudaSuccess ||
         ctx->Rt.ensure(12 * sizeof(double)) != cudaSuccess) {
         hgmm_destroy(ctx);
@@ -253,6 +261,8 @@ int hgmm_destroy(hgmm_ctx* ctx) {
     }
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     if (ctx->h_dbl) cudaFreeHost(ctx->h_dbl);
+    if (ctx->h_params) cudaFreeHost(ctx->h_params);
+    if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
@@ -333,9 +343,7 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     CK(cudaSetDevice(ctx->device));
     const int Jp = (J + 31) / 32 * 32;
     const size_t ce = cov_elems(cfg->cov_type);
-    CK(ctx->f_means.ensure((size_t)Jp * 3 * sizeof(float)));
-    CK(ctx->f_covs.ensure((size_t)Jp * 9 * sizeof(float)));
-    CK(ctx->f_weights.ensure((size_t)Jp * sizeof(float)));
+    CK(ctx->f_means.ensure((size_t)Jp * 13 * sizeof(float)));     // means [Jp,3] | covs [Jp,9] | weights [Jp]: one upload
     CK(ctx->f_invcov.ensure((size_t)Jp * 3 * sizeof(float)));
     CK(ctx->f_packed.ensure((size_t)Jp * sizeof(PackedComp)));
     const size_t acc_n = kAccHdr + (size_t)Jp * kMom;
@@ -343,20 +351,23 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     CK(ctx->hist.ensure((size_t)(cfg->max_iter + 1) * sizeof(double)));
     FlatModel& m = ctx->fm;
     m.J = J; m.Jp = Jp; m.cov_type = cfg->cov_type; m.flavor = cfg->flavor; m.sigma_bug = cfg->sigma_bug; m.tol = cfg->tol;
-    m.means = ctx->f_means.as<float>(); m.covs = ctx->f_covs.as<float>(); m.weights = ctx->f_weights.as<float>();
+    m.means = ctx->f_means.as<float>(); m.covs = m.means + (size_t)Jp * 3; m.weights = m.means + (size_t)Jp * 12;
     m.inv_cov = ctx->f_invcov.as<float>(); m.packed = ctx->f_packed.as<PackedComp>();
     CK(ctx->cref.ensure((size_t)(Jp / 32 + 4) * sizeof(float)));
     m.cref_blocks = ctx->cref.as<float>();
     cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(m.means, init_means, (size_t)J * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(m.covs, init_covs, (size_t)J * ce * sizeof(float), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(m.weights, init_weights, (size_t)J * sizeof(float), cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(ctx->acc.p, 0, acc_n * sizeof(double), s));
-    CK(cudaMemsetAsync(ctx->ctrl.p, 0, 8 * sizeof(int), s));
+    // initial parameters: gathered in the pinned staging block (the previous fit ended with a stream synchronise, so it is
+    // free), ONE asynchronous upload; the pack kernel also clears the control words -- 2 stream operations before the first
+    // sweep instead of 7
+    memcpy(ctx->h_params, init_means, (size_t)J * 3 * sizeof(float));
+    memcpy(ctx->h_params + (size_t)Jp * 3, init_covs, (size_t)J * ce * sizeof(float));
+    memcpy(ctx->h_params + (size_t)Jp * 12, init_weights, (size_t)J * sizeof(float));
+    CK(cudaMemcpyAsync(m.means, ctx->h_params, (size_t)Jp * 13 * sizeof(float), cudaMemcpyHostToDevice, s));
     CK(ctx->done_at.ensure((size_t)(cfg->max_iter + 2) * sizeof(int)));
-    CK(cudaMemsetAsync(ctx->done_at.p, 0, (size_t)(cfg->max_iter + 2) * sizeof(int), s));
     int* done_at = ctx->done_at.as<int>();
-    launch_flat_pack(m, 1, s);
+    const bool need_acc = cfg->reserved == 1 || cfg->reserved == 3 || (ctx->nranks > 1 && !ctx->p2p_ready);
+    if (need_acc) CK(cudaMemsetAsync(ctx->acc.p, 0, acc_n * sizeof(double), s));
+    launch_flat_pack_init(m, ctx->ctrl.as<int>(), done_at, cfg->max_iter + 2, s);
     ctx->launches += 1;
     // kernel variant: reserved == 1 selects the first-generation two-phase kernel (fp64 atomics), else the
     // register-resident single-evaluation kernel with deterministic partial rows
@@ -428,14 +439,16 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     CK(cudaEventRecord(ctx->ev1, s));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (out_means) CK(cudaMemcpyAsync(out_means, m.means, (size_t)J * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (out_covs) CK(cudaMemcpyAsync(out_covs, m.covs, (size_t)J * ce * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (out_weights) CK(cudaMemcpyAsync(out_weights, m.weights, (size_t)J * sizeof(float), cudaMemcpyDeviceToHost, s));
+    const bool want_model = out_means || out_covs || out_weights;      // one download into the pinned block, split on the host
+    if (want_model) CK(cudaMemcpyAsync(ctx->h_params, m.means, (size_t)Jp * 13 * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (out_inv_cov && cfg->flavor != HGMM_FLAVOR_CPP)
         CK(cudaMemcpyAsync(out_inv_cov, m.inv_cov, (size_t)J * (ce == 1 ? 1 : 3) * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (out_ll && cfg->max_iter > 0)
         CK(cudaMemcpyAsync(out_ll, ctx->hist.p, (size_t)cfg->max_iter * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (out_means) memcpy(out_means, ctx->h_params, (size_t)J * 3 * sizeof(float));
+    if (out_covs) memcpy(out_covs, ctx->h_params + (size_t)Jp * 3, (size_t)J * ce * sizeof(float));
+    if (out_weights) memcpy(out_weights, ctx->h_params + (size_t)Jp * 12, (size_t)J * sizeof(float));
     if (out_iters) *out_iters = ctx->h_ctrl[1];
     if (ctx->h_ctrl[7]) FAIL(HGMM_ERR_NCCL, "peer-memory exchange timed out: a rank is missing or the ranks' call sequences differ");
     float ms = 0.f;
@@ -588,23 +601,54 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
         const PackedComp* level_packed = t.packed + level_base_h(l);
         bool done = false;
         int it = 0;
-        while (!done) {
-            for (int b = 0; b < batch; ++b, ++it) {
-                CK(launch_tree_estep(w[cur], t, l, acc, chunks_bound, nchunks_dev, done_at + it, cfg->reserved == 1, s));
-                r = allreduce(ctx, acc, kAccHdr + (size_t)cnt * kMom);
-                if (r != HGMM_OK) return r;
-                launch_tree_mstep(t, l, acc, (double)ctx->n_total, cfg->ld, ctrl, done_at, it, fast_ll ? 1 : 0, qstate, cfg->ls,
-                                  max_iters, s);
-                ctx->launches += 2;
-                if (!fast_ll) {
-                    launch_tree_zero_ll(acc, done_at + it, s);
-                    CK(launch_level_ll(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), n, level_packed, (int)cnt, acc,
-                                       done_at + it, ctx->num_sms, s));
-                    r = allreduce(ctx, acc, 1);
-                    if (r != HGMM_OK) return r;
-                    launch_tree_converge(acc, ctrl, done_at, it, qstate, cfg->ls, max_iters, s);
-                    ctx->launches += 3;
+        auto enqueue_iteration = [&](int* prog) -> int {
+            cudaError_t e = launch_tree_estep(w[cur], t, l, acc, chunks_bound, nchunks_dev, done_at + it, cfg->reserved == 1, s);
+            if (e != cudaSuccess) { ctx->err = std::string("tree E-step launch: ") + cudaGetErrorString(e); return HGMM_ERR_CUDA; }
+            int rr = allreduce(ctx, acc, kAccHdr + (size_t)cnt * kMom);
+            if (rr != HGMM_OK) return rr;
+            launch_tree_mstep(t, l, acc, (double)ctx->n_total, cfg->ld, ctrl, done_at, it, fast_ll ? 1 : 0, qstate, cfg->ls, max_iters,
+                              prog, s);
+            ctx->launches += 2;
+            if (!fast_ll) {
+                launch_tree_zero_ll(acc, done_at + it, s);
+                e = launch_level_ll(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), n, level_packed, (int)cnt, acc,
+                                    done_at + it, ctx->num_sms, s);
+                if (e != cudaSuccess) { ctx->err = std::string("level log-likelihood launch: ") + cudaGetErrorString(e); return HGMM_ERR_CUDA; }
+                rr = allreduce(ctx, acc, 1);
+                if (rr != HGMM_OK) return rr;
+                launch_tree_converge(acc, ctrl, done_at, it, qstate, cfg->ls, max_iters, prog, s);
+                ctx->launches += 3;
+            }
+            ++it;
+            return HGMM_OK;
+        };
+        if (ctx->nranks <= 1) {
+            // single rank: no stream synchronise inside the level.  The kernel that evaluates the stopping rule also writes
+            // (converged, iterations retired) to host-mapped memory; the host keeps at most `ahead` iterations in flight and
+            // stops enqueuing when it sees the flag (iterations already enqueued are no-ops through done_at).
+            volatile int* prog = ctx->h_prog;
+            prog[0] = 0;
+            prog[1] = 0;
+            const int ahead = 6;
+            const auto t_start = std::chrono::steady_clock::now();
+            while (true) {
+                bool stalled = false;
+                while (it - prog[0] >= ahead && !prog[1]) {
+                    if (std::chrono::steady_clock::now() - t_start > std::chrono::seconds(120)) { stalled = true; break; }
                 }
+                if (stalled || prog[1] || it >= max_iters + batch) break;
+                r = enqueue_iteration(ctx->d_prog);
+                if (r != HGMM_OK) return r;
+            }
+            CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            done = ctx->h_ctrl[0] != 0;
+            if (!done) FAIL(HGMM_ERR_CUDA, "tree build made no progress (device error?)");
+        }
+        while (!done) {       // several ranks: every rank must enqueue the same number of all-reduces -> fixed batches
+            for (int b = 0; b < batch; ++b) {
+                r = enqueue_iteration(nullptr);
+                if (r != HGMM_OK) return r;
             }
             CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));

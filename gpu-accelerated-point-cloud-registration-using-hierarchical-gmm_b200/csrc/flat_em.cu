@@ -74,8 +74,13 @@ __device__ __forceinline__ void block_max_c2(float c2, float* __restrict__ cref_
     if ((threadIdx.x & 31) == 0 && slot < n_slots) cref_blocks[slot] = v;
 }
 
-__global__ void __launch_bounds__(128) flat_pack_kernel(FlatModel m, int first) {
+__global__ void __launch_bounds__(128) flat_pack_kernel(FlatModel m, int first, int* __restrict__ ctrl, int* __restrict__ done_at,
+                                                        int n_done) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ctrl) {                                         // start of a fit: clear the control words and the per-iteration flags
+        if (j < 8) ctrl[j] = 0;
+        for (int i = j; i < n_done; i += gridDim.x * blockDim.x) done_at[i] = 0;
+    }
     PackedComp p = pack_full(-INFINITY, 0, 0, 0, Sym3{1, 0, 0, 1, 0, 1}, false, 0.0);     // padding: dead component
     if (j < m.J) {
         const double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
@@ -602,7 +607,10 @@ void launch_aos_to_soa_transform(const float* xyz, int64_t n, const double* Rt, 
     aos_to_soa_transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(xyz, n, Rt, x, y, z);
 }
 void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s) {
-    flat_pack_kernel<<<(m.Jp + 127) / 128, 128, 0, s>>>(m, first);
+    flat_pack_kernel<<<(m.Jp + 127) / 128, 128, 0, s>>>(m, first, nullptr, nullptr, 0);
+}
+void launch_flat_pack_init(const FlatModel& m, int* ctrl, int* done_at, int n_done, cudaStream_t s) {
+    flat_pack_kernel<<<(m.Jp + 127) / 128, 128, 0, s>>>(m, 1, ctrl, done_at, n_done);
 }
 void launch_flat_reduce_finalize(const FlatModel& m, const float* partial, const double* rowaux, int rows, int* ctrl, int* done_at,
                                  int it, double* ll_hist, double n_total, cudaStream_t s) {

@@ -49,6 +49,23 @@ __device__ __forceinline__ void mbar_arrive7(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// wait with a long suspend-time hint: the warps that share the left-over column are idle ~3/4 of the time and would otherwise
+// spend issue slots of their sub-partition re-polling (profiles/r01_em_flat7_ncu_full.txt: SYNCS + YIELD + BRA = 10 % of the
+// instructions issued); the wait still returns as soon as the phase completes
+__device__ __forceinline__ void mbar_wait7(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT7_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAIT7_DONE;\n\t"
+        "bra WAIT7_LOOP;\n\t"
+        "WAIT7_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
+
 template <int P>
 __global__ void __launch_bounds__(512, 1) em_flat7_kernel(const float* __restrict__ px, const float* __restrict__ py,
                                                           const float* __restrict__ pz, int n,
@@ -181,7 +198,7 @@ __global__ void __launch_bounds__(512, 1) em_flat7_kernel(const float* __restric
             const int b = g & 1;
             const int c0 = c * CH;
             const int ch = min(CH, cn - c0);
-            mbar_wait(&bars[b], (g >> 1) & 1);
+            mbar_wait7(&bars[b], (g >> 1) & 1);
             // ---------------- finish (every warp, lane = point): fold the P column sums in a fixed order
             const bool valid = lane < ch;
             float v = 0.f;

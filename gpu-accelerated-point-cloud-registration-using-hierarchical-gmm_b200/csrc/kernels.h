@@ -60,6 +60,7 @@ struct TreeWork {
 void launch_aos_to_soa(const float* xyz, int64_t n, float* x, float* y, float* z, cudaStream_t s);
 void launch_aos_to_soa_transform(const float* xyz, int64_t n, const double* Rt, float* x, float* y, float* z, cudaStream_t s);
 void launch_flat_pack(const FlatModel& m, int first, cudaStream_t s);
+void launch_flat_pack_init(const FlatModel& m, int* ctrl, int* done_at, int n_done, cudaStream_t s);
 void launch_flat_finalize(const FlatModel& m, const double* acc, int* ctrl, int* done_at, int it, double* ll_hist, double n_total,
                           cudaStream_t s);
 void launch_flat_reduce_finalize(const FlatModel& m, const float* partial, const double* rowaux, int rows, int* ctrl, int* done_at,
@@ -107,8 +108,9 @@ void launch_tree_pack_all(const TreeModel& t, cudaStream_t s);
 cudaError_t launch_tree_estep(const TreeWork& w, const TreeModel& t, int level, double* acc, int n_chunks_bound,
                               const int* n_chunks_dev, const int* done_flag, int scalar_variant, cudaStream_t s);
 void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_total, float ld, int* ctrl, int* done_at, int it,
-                       int merge_converge, double* qstate, float ls, int max_iters, cudaStream_t s);
-void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, cudaStream_t s);
+                       int merge_converge, double* qstate, float ls, int max_iters, int* prog, cudaStream_t s);
+void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, int* prog,
+                          cudaStream_t s);
 void launch_tree_zero_ll(double* acc, const int* done_flag, cudaStream_t s);
 void launch_tree_cplx(const TreeModel& t, cudaStream_t s);
 void launch_tree_current(const TreeWork& w, int n, int level, int64_t* current, cudaStream_t s);

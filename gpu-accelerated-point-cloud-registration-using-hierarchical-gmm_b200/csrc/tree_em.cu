@@ -239,14 +239,18 @@ __global__ void __launch_bounds__(256, 3) tree_estep2_kernel(const float* __rest
                                                              const PackedComp* __restrict__ packed_level,
                                                              double* __restrict__ acc, uint8_t* __restrict__ slot,
                                                              const int* __restrict__ done_flag) {
-    if (*done_flag) return;
+    // programmatic dependent launch (the build is launch-bound: ~3 us of work per EM iteration): this grid may be scheduled
+    // while the M-step of the previous iteration drains; everything that kernel wrote is read after the wait, from L2
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (__ldcg(done_flag)) return;
     __shared__ float s_part[8][8 * kMom];
     __shared__ int s_parent[8];
     __shared__ double s_ll[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cp = lane >> 3, pl = lane & 7;
     const int chunk = blockIdx.x * 8 + warp;
-    const int n_chunks = *n_chunks_dev;
+    const int n_chunks = __ldcg(n_chunks_dev);
     double ll = 0.0;
     int my_parent = -1;
     if (chunk < n_chunks) {
@@ -257,8 +261,8 @@ __global__ void __launch_bounds__(256, 3) tree_estep2_kernel(const float* __rest
         float2 nmx, nmy, nmz, c2, axx, ayy, azz, axy, axz, ayz;
         {
             const float4* a4 = reinterpret_cast<const float4*>(packed_level + 8 * (size_t)p + 2 * cp);
-            const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), a2 = __ldg(a4 + 2);
-            const float4 b0 = __ldg(a4 + 3), b1 = __ldg(a4 + 4), b2 = __ldg(a4 + 5);
+            const float4 a0 = __ldcg(a4), a1 = __ldcg(a4 + 1), a2 = __ldcg(a4 + 2);
+            const float4 b0 = __ldcg(a4 + 3), b1 = __ldcg(a4 + 4), b2 = __ldcg(a4 + 5);
             nmx = make_float2(-a0.x, -b0.x); nmy = make_float2(-a0.y, -b0.y); nmz = make_float2(-a0.z, -b0.z);
             c2 = make_float2(a0.w, b0.w);
             axx = make_float2(a1.x, b1.x); ayy = make_float2(a1.y, b1.y); azz = make_float2(a1.z, b1.z);
@@ -369,28 +373,39 @@ __global__ void __launch_bounds__(256, 3) tree_estep2_kernel(const float* __rest
 // also applies the |q - prevQ| < ls rule to acc[0] (complete: the E-step has finished) and arms done_at[it+1].
 __global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __restrict__ acc, double n_total, float ld,
                                   int* __restrict__ ctrl, int* __restrict__ done_at, int it, int merge_converge,
-                                  double* __restrict__ qstate, float ls, int max_iters) {
-    const bool done = done_at[it] != 0;
+                                  double* __restrict__ qstate, float ls, int max_iters, volatile int* prog) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const bool done = __ldcg(done_at + it) != 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (done) {
             done_at[it + 1] = 1;
+            if (prog && merge_converge) prog[0] = it + 1;
         } else if (merge_converge) {
-            const double q = acc[0];
+            const double q = __ldcg(acc);                     // L2 loads: written by the previous kernels of the PDL chain
             acc[0] = 0.0;
-            const int n_it = ctrl[1] + 1;
+            const int n_it = __ldcg(ctrl + 1) + 1;
             ctrl[1] = n_it;
             qstate[1] = q;
-            const bool conv = fabs(q - qstate[0]) < (double)ls || n_it >= max_iters;
+            const bool conv = fabs(q - __ldcg(qstate)) < (double)ls || n_it >= max_iters;
             qstate[0] = q;
             ctrl[0] = conv ? 1 : 0;
             done_at[it + 1] = conv ? 1 : 0;
+            if (prog) {                                   // host-mapped progress words: [1] converged, then [0] iterations retired
+                prog[1] = conv ? 1 : 0;
+                __threadfence_system();
+                prog[0] = it + 1;
+            }
         }
     }
     if (done) return;
     const int local = blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= count) return;
     const int j = lb + local;
-    double* A = acc + kAccHdr + (size_t)local * kMom;
+    double* Ag = acc + kAccHdr + (size_t)local * kMom;
+    double A[kMom];
+#pragma unroll
+    for (int k = 0; k < kMom; ++k) A[k] = __ldcg(Ag + k);
     const double M0 = A[0];
     // mlEstimator (hgmm_cupy_cpu_working.py:109-119): blank node if M0 < ld
     if (M0 >= (double)ld) {
@@ -416,14 +431,15 @@ __global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __rest
         t.packed[j] = pack_full(-INFINITY, 0, 0, 0, Sym3{1, 0, 0, 1, 0, 1}, false, 1e-15);
     }
 #pragma unroll
-    for (int k = 0; k < kMom; ++k) A[k] = 0.0;
+    for (int k = 0; k < kMom; ++k) Ag[k] = 0.0;
 }
 
 // |q - prevQ| < ls with prevQ = 0 at level start (hgmm_gpu.py:520,533-535).  qstate: [0] prevQ, [1] last q.
 __global__ void tree_converge_kernel(double* __restrict__ acc, int* __restrict__ ctrl, int* __restrict__ done_at, int it,
-                                     double* __restrict__ qstate, float ls, int max_iters) {
+                                     double* __restrict__ qstate, float ls, int max_iters, volatile int* prog) {
     if (done_at[it]) {
         done_at[it + 1] = 1;
+        if (prog) prog[0] = it + 1;
         return;
     }
     const double q = acc[0];
@@ -435,6 +451,11 @@ __global__ void tree_converge_kernel(double* __restrict__ acc, int* __restrict__
     qstate[0] = q;
     ctrl[0] = conv ? 1 : 0;
     done_at[it + 1] = conv ? 1 : 0;
+    if (prog) {
+        prog[1] = conv ? 1 : 0;
+        __threadfence_system();
+        prog[0] = it + 1;
+    }
 }
 
 __global__ void tree_zero_ll_kernel(double* __restrict__ acc, const int* __restrict__ done_flag) {
@@ -666,9 +687,19 @@ cudaError_t launch_tree_estep(const TreeWork& w, const TreeModel& t, int level, 
     if (n_chunks_bound <= 0) return cudaSuccess;
     const int grid = (n_chunks_bound + 7) / 8;
     if (!scalar_variant) {
-        tree_estep2_kernel<<<grid, 256, 0, s>>>(w.x, w.y, w.z, w.chunk_parent, w.chunk_start, w.chunk_len, n_chunks_dev,
-                                                t.packed + level_base(level), acc, w.slot, done_flag);
-        return cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const PackedComp* pl = t.packed + level_base(level);
+        return cudaLaunchKernelEx(&cfg, tree_estep2_kernel, (const float*)w.x, (const float*)w.y, (const float*)w.z,
+                                  (const int*)w.chunk_parent, (const int*)w.chunk_start, (const int*)w.chunk_len, n_chunks_dev, pl, acc,
+                                  w.slot, done_flag);
     }
     tree_estep_kernel<<<grid, 256, 0, s>>>(w.x, w.y, w.z, w.chunk_parent, w.chunk_start, w.chunk_len, n_chunks_dev,
                                            t.packed + level_base(level), acc, w.slot, done_flag);
@@ -676,14 +707,24 @@ cudaError_t launch_tree_estep(const TreeWork& w, const TreeModel& t, int level, 
 }
 
 void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_total, float ld, int* ctrl, int* done_at, int it,
-                       int merge_converge, double* qstate, float ls, int max_iters, cudaStream_t s) {
+                       int merge_converge, double* qstate, float ls, int max_iters, int* prog, cudaStream_t s) {
     const int cnt = level_count(level);
-    tree_mstep_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(t, level_base(level), cnt, acc, n_total, ld, ctrl, done_at, it, merge_converge,
-                                                        qstate, ls, max_iters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((cnt + 127) / 128);
+    cfg.blockDim = dim3(128);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, tree_mstep_kernel, t, level_base(level), cnt, acc, n_total, ld, ctrl, done_at, it, merge_converge, qstate,
+                       ls, max_iters, (volatile int*)prog);
 }
 
-void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, cudaStream_t s) {
-    tree_converge_kernel<<<1, 1, 0, s>>>(acc, ctrl, done_at, it, qstate, ls, max_iters);
+void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, int* prog,
+                          cudaStream_t s) {
+    tree_converge_kernel<<<1, 1, 0, s>>>(acc, ctrl, done_at, it, qstate, ls, max_iters, (volatile int*)prog);
 }
 void launch_tree_zero_ll(double* acc, const int* done_flag, cudaStream_t s) { tree_zero_ll_kernel<<<1, 1, 0, s>>>(acc, done_flag); }
 void launch_tree_cplx(const TreeModel& t, cudaStream_t s) { tree_cplx_kernel<<<(t.nt + 127) / 128, 128, 0, s>>>(t); }

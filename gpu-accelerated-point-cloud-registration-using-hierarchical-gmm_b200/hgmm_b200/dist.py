@@ -84,9 +84,42 @@ def attach_communicator(engine, p2p=None):
         dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0 and engine.p2p_enabled:
+        ok = int(flag.item()) == 1
+        if ok:
+            ok = _p2p_self_test(engine, rank, world, dev)
+        if not ok and engine.p2p_enabled:
             engine.p2p_detach()
     return rank, world
+
+
+def _p2p_self_test(engine, rank, world, dev):
+    """two EM iterations of a small mixture through the peer-memory exchange on every rank: all ranks must succeed and hold
+    bit-identical replicas, otherwise all of them fall back to NCCL (collective decision: every rank reaches both
+    all_reduce calls whatever happened locally)."""
+    import torch
+    import torch.distributed as dist
+    from ._lib import HgmmError
+    rng = np.random.default_rng(1234 + rank)
+    pts = rng.normal(0.0, 1.0, (4096, 3)).astype(np.float32)
+    J = 64
+    mu0 = np.random.default_rng(99).normal(0.0, 1.0, (J, 3)).astype(np.float32)     # identical on every rank
+    cov0 = np.tile(np.eye(3, dtype=np.float32), (J, 1, 1))
+    w0 = np.full(J, 1.0 / J, np.float32)
+    good, digest = 1, np.zeros(4, np.float64)
+    try:
+        engine.set_points(pts)
+        r = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=2)
+        digest = np.array([r["means"].astype(np.float64).sum(), r["covs"].astype(np.float64).sum(),
+                           r["weights"].astype(np.float64).sum(), float(r["ll"][-1])])
+        if not np.isfinite(digest).all():
+            good = 0
+    except HgmmError:
+        good = 0
+    lo = torch.from_numpy(np.concatenate([[float(good)], digest])).to(dev)
+    hi = lo.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(lo[0].item() == 1.0 and bool((lo[1:] == hi[1:]).all().item()))
 
 
 def allreduce_moments_host(local_moments):
