@@ -8,6 +8,8 @@ Thin ctypes wrapper that keeps the reference's Python surface (SURVEY.md section
                                                                      (src/python/hgmm/hgmm_gpu.py)
     gmmreg   : registration_gmmreg, RigidGMMReg, L2DistRegistration, RigidCostFunction, GMM_GPU (older diag fitter)
                                                                      (src/python/gmmreg_gpu/{gmmreg,cost_functions,gmm,gmm_impl}.py)
+    stream   : StreamingSegmenter -- re-fit every k frames, hard-assign every frame      (src/python/gmm_waymo/src/run_gmm_waymo_gpu.py:39-50)
+    io       : read_ply, read_pcd -- the viewers' / drivers' cloud readers              (src/c++/main.cpp:45-79, main_reg.cpp:106-161)
     dist     : point sharding + NCCL communicator bootstrap over torch.distributed
     engine   : Engine, the object wrapper over the C ABI (include/hgmm.h)
 
@@ -15,6 +17,6 @@ All compute runs in the CUDA library; there is no CPU fallback and nothing here 
 """
 from ._lib import HgmmError, LIB_PATH  # noqa: F401
 from .engine import Engine  # noqa: F401
-from . import gmm_impl, gmm, hgmm, gmmreg, dist  # noqa: F401
+from . import gmm_impl, gmm, hgmm, gmmreg, dist, stream, io  # noqa: F401
 
-__all__ = ["Engine", "HgmmError", "gmm_impl", "gmm", "hgmm", "gmmreg", "dist", "LIB_PATH"]
+__all__ = ["Engine", "HgmmError", "gmm_impl", "gmm", "hgmm", "gmmreg", "dist", "stream", "io", "LIB_PATH"]

@@ -68,6 +68,8 @@ SIGNATURES = {
     "hgmm_comm_unique_id": (C.c_int, [_VP]),
     "hgmm_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "hgmm_comm_destroy": (C.c_int, [_VP]),
+    "hgmm_io_read_ply": (C.c_int, [C.c_char_p, C.c_int32, _VP, C.c_int64, _VP]),
+    "hgmm_io_read_pcd": (C.c_int, [C.c_char_p, _VP, C.c_int64, _VP]),
     "hgmm_p2p_export": (C.c_int, [_VP, _VP]),
     "hgmm_p2p_attach": (C.c_int, [_VP, _VP, C.c_int32]),
     "hgmm_p2p_detach": (C.c_int, [_VP]),

@@ -15,6 +15,7 @@
  *   hgmm_reg_mstep         GMMTree.maximization_step         src/python/hgmm/hgmm_gpu.py:729-752
  *   hgmm_register_tree     GMMTree.registration              src/python/hgmm/hgmm_gpu.py:754-768
  *                          GMMRegistration::pointCloudRegisterGPU (empty stub) gmm_reg.cu:54-56
+ *   hgmm_io_read_ply/pcd   readData  src/c++/main.cpp:45-79, readPointCloud  src/c++/main_reg.cpp:106-161
  *   hgmm_l2_*              RigidCostFunction / L2DistRegistration  src/python/gmmreg_gpu/cost_functions.py:29-69, gmmreg.py:62-121
  *   hgmm_fill_vbo          scanRegistration::copyBoidsToVBO  src/c++/gmm_fit/gmm_kernels.cu:532-542
  *                          GMMRegistration::copyBoidsToVBO   src/c++/gmm_registration/gmm_reg.cu:45-52
@@ -43,6 +44,7 @@ extern "C" {
 #define HGMM_ERR_STATE (-3)        /* call order (no points / no tree yet) */
 #define HGMM_ERR_NCCL (-4)         /* NCCL unavailable or failed */
 #define HGMM_ERR_NUMERIC (-5)      /* singular system in the registration solve */
+#define HGMM_ERR_IO (-6)           /* file cannot be opened / is not in a supported format */
 
 #define HGMM_MEM_HOST 0
 #define HGMM_MEM_DEVICE 1
@@ -162,6 +164,17 @@ int hgmm_l2_cost_grad(hgmm_ctx* ctx, const double* theta, double sigma, double* 
  * 1 = iteration limit, 2 = line search failed (the end point is still the best one found) */
 int hgmm_l2_optimize(hgmm_ctx* ctx, double* theta, double sigma, int32_t max_iter, double gtol, double* out_f,
                      int32_t* out_iters, int32_t* out_nfev, int32_t* out_status);
+
+/* ---- ingestion: the callers' step in front of the path (host only, no context, no CUDA call) ----
+ * replaces readData  src/c++/main.cpp:45-79 (HGMM_PLY_VIEWER_FIT; its hard-coded similarity transforms are not applied),
+ * readPointCloud  src/c++/main_reg.cpp:106-161 (HGMM_PLY_VIEWER_REG), and the Open3D read_point_cloud calls of the Python
+ * drivers for `DATA ascii|binary` PCD files (src/python/hgmm/hgmm_gpu.py:813-822).  out_xyz: [capacity,3] packed float32 or
+ * NULL with capacity 0; *out_n = points in the file (may exceed capacity: call again with a larger buffer). */
+#define HGMM_PLY_HEADER 0          /* header-driven: `element vertex N`, x y z first, ASCII */
+#define HGMM_PLY_VIEWER_FIT 1
+#define HGMM_PLY_VIEWER_REG 2
+int hgmm_io_read_ply(const char* path, int32_t mode, float* out_xyz, int64_t capacity, int64_t* out_n);
+int hgmm_io_read_pcd(const char* path, float* out_xyz, int64_t capacity, int64_t* out_n);
 
 /* ---- viewer glue ---- */
 /* writes 4 floats per point: pos = (-x, -y, -z)/scene_scale, 1 ; col = rgb + 0.3, 1.
