@@ -10,6 +10,7 @@
 // stopping rules run on the device, and the host only polls a 2-int control word.
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
@@ -131,6 +132,7 @@ struct hgmm_ctx {
     bool have_tree = false;
     DevBuf t_pi, t_mu, t_cov, t_cplx, t_packed, t_init;
     DevBuf wx[2], wy[2], wz[2], wperm[2], wpnode[2], wslot[2], wcpar[2], wcstart[2], wclen[2];
+    DevBuf gbar;                // persistent level kernel: grid barrier words
     DevBuf p_group, p_tilecnt, p_tileoff, p_segbase, p_seg0, p_seg1, p_chunkcnt, p_chunkoff, nchunks, current;
 
     // registration
@@ -252,7 +254,7 @@ int hgmm_destroy(hgmm_ctx* ctx) {
                      &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->done_at, &ctx->partial, &ctx->rowaux, &ctx->cref, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
                      &ctx->t_cplx, &ctx->t_packed, &ctx->t_init, &ctx->p_group, &ctx->p_tilecnt, &ctx->p_tileoff, &ctx->p_segbase,
                      &ctx->p_seg0, &ctx->p_seg1, &ctx->p_chunkcnt, &ctx->p_chunkoff, &ctx->nchunks, &ctx->current, &ctx->tx, &ctx->ty,
-                     &ctx->tz, &ctx->racc, &ctx->Rt, &ctx->l2buf};
+                     &ctx->tz, &ctx->racc, &ctx->Rt, &ctx->l2buf, &ctx->gbar};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < 2; ++i) {
         DevBuf* w[] = {&ctx->wx[i], &ctx->wy[i], &ctx->wz[i], &ctx->wperm[i], &ctx->wpnode[i], &ctx->wslot[i], &ctx->wcpar[i],
@@ -622,7 +624,18 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
             ++it;
             return HGMM_OK;
         };
-        if (ctx->nranks <= 1) {
+        static const bool persist = getenv("HGMM_TREE_PERSIST") && getenv("HGMM_TREE_PERSIST")[0] == '1';     // draft switch
+        if (persist && ctx->nranks <= 1 && fast_ll && cfg->reserved != 1) {
+            // DRAFT (tree_level_kernel): the whole EM loop of the level in one cooperative launch
+            CK(ctx->gbar.ensure(2 * sizeof(unsigned)));
+            CK(cudaMemsetAsync(ctx->gbar.p, 0, 2 * sizeof(unsigned), s));
+            CK(launch_tree_level(w[cur], t, l, acc, chunks_bound, nchunks_dev, (double)ctx->n_total, cfg->ld, cfg->ls, max_iters, ctrl,
+                                 qstate, ctx->gbar.as<unsigned>(), ctx->num_sms, s));
+            ctx->launches += 1;
+            CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            done = true;
+        } else if (ctx->nranks <= 1) {
             // single rank: no stream synchronise inside the level.  The kernel that evaluates the stopping rule also writes
             // (converged, iterations retired) to host-mapped memory; the host keeps at most `ahead` iterations in flight and
             // stops enqueuing when it sees the flag (iterations already enqueued are no-ops through done_at).

@@ -636,14 +636,11 @@ static cudaError_t launch_em_flat_t(const float* x, const float* y, const float*
                                     const int* ctrl, int num_sms, cudaStream_t s) {
     constexpr int KS = 256 / (TP / 2);
     const size_t smem = (size_t)m.Jp * sizeof(PackedComp) + (size_t)TP * 16 + (size_t)KS * TP * 8;
-    static bool attr_done = false;
-    static size_t attr_smem = 0;
+    static DeviceOnce once;
     auto kern = em_flat_kernel<TP, JT>;
-    if (!attr_done || smem > attr_smem) {
+    if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
         if (e != cudaSuccess) return e;
-        attr_done = true;
-        attr_smem = 200 * 1024;
     }
     const int nTiles = (n + TP - 1) / TP;
     int occ = 1;

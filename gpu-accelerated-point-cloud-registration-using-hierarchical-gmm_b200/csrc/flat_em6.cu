@@ -284,12 +284,9 @@ static int flat6_chunk(int T, int smem_optin) {
 
 cudaError_t launch_em_flat6(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
                             int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s) {
-    static int smem_optin = 0;
-    if (!smem_optin) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || smem_optin <= 0)
-            smem_optin = 227 * 1024;
+    const int smem_optin = device_smem_optin();
+    static DeviceOnce once;
+    if (once.first()) {
         cudaFuncSetAttribute(em_flat6_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
         cudaFuncSetAttribute(em_flat6_kernel<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
         cudaFuncSetAttribute(em_flat6_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);

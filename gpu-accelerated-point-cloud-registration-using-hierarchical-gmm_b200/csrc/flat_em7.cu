@@ -388,11 +388,10 @@ static void flat7_shape(int C, int smem_optin, int* CH, int* SB) {
 template <int P>
 static cudaError_t launch7(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
                            int grid, float* partial, double* rowaux, const int* done_flag, int smem_optin, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;      // one per instantiation P
+    if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(em_flat7_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     int CH, SB;
     flat7_shape(P * 32, smem_optin, &CH, &SB);
@@ -416,13 +415,7 @@ static cudaError_t launch7(const float* x, const float* y, const float* z, int n
 
 cudaError_t launch_em_flat7(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
                             int P, int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s) {
-    static int smem_optin = 0;
-    if (!smem_optin) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || smem_optin <= 0)
-            smem_optin = 227 * 1024;
-    }
+    const int smem_optin = device_smem_optin();
 #define HGMM_F7(PP) case PP: return launch7<PP>(x, y, z, n, m, cref_blocks, grid, partial, rowaux, done_flag, smem_optin, s);
     switch (P) {
         HGMM_F7(5) HGMM_F7(6) HGMM_F7(7) HGMM_F7(8) HGMM_F7(9) HGMM_F7(10) HGMM_F7(11) HGMM_F7(12)

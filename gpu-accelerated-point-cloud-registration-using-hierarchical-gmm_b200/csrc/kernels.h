@@ -8,6 +8,32 @@ namespace hgmm {
 
 struct PackedComp;
 
+// Function attributes (cudaFuncSetAttribute) and device limits are PER DEVICE: a process may own contexts on several devices
+// (include/hgmm.h: hgmm_create(device)), so one-time setup is remembered per device ordinal, never in a process-wide flag.
+struct DeviceOnce {
+    bool done[64] = {};
+    bool first() {               // true exactly once per current device
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+inline int device_smem_optin() {  // opt-in shared memory per block of the current device
+    static int cache[64] = {};
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (!cache[d]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, d) != cudaSuccess || v <= 0) v = 227 * 1024;
+        cache[d] = v;
+    }
+    return cache[d];
+}
+
 constexpr int kMaxFlatJ = 1024;          // fused flat kernel keeps <= 4 components per thread in registers
 
 struct FlatModel {
@@ -111,6 +137,9 @@ void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_tota
                        int merge_converge, double* qstate, float ls, int max_iters, int* prog, cudaStream_t s);
 void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, int* prog,
                           cudaStream_t s);
+cudaError_t launch_tree_level(const TreeWork& w, const TreeModel& t, int level, double* acc, int n_chunks_bound,
+                              const int* n_chunks_dev, double n_total, float ld, float ls, int max_iters, int* ctrl, double* qstate,
+                              unsigned* gbar, int num_sms, cudaStream_t s);
 void launch_tree_zero_ll(double* acc, const int* done_flag, cudaStream_t s);
 void launch_tree_cplx(const TreeModel& t, cudaStream_t s);
 void launch_tree_current(const TreeWork& w, int n, int level, int64_t* current, cudaStream_t s);

@@ -7,6 +7,8 @@
 //   svd + Procrustes use (host, ICP only)             src/c++/common/svd3.h:355-401, icp/icp_kernel.cu:697-731
 //   GMMRegistration::pointCloudRegisterGPU            src/c++/gmm_registration/gmm_reg.cu:54-56 (empty stub)
 //   kernCopyPositionsToVBO / kernCopyVelocitiesToVBO  src/c++/gmm_registration/gmm_reg_kernels.cu:3-41
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -123,6 +125,88 @@ __global__ void __launch_bounds__(256) reg_estep_kernel(const float* __restrict_
             for (int k = 0; k < nm; ++k)
                 if (v[k] != 0.0) atomicAdd(racc + (size_t)node * kRegMom + k, v[k]);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// E-step, second generation (DRAFT: compiled, not yet run on a GPU -- selected only by HGMM_REG_ESTEP2=1).
+// reg_estep_kernel is a latency-bound single wave (profiles/r01_reg_estep_ncu_full.txt: issue-active 9 %, top stalls
+// short_scoreboard / barrier / long_scoreboard): every thread walks its own point and reads the 8 children of its own parent,
+// so from level 1 on a warp-wide LDG.128 touches up to 32 different lines (24 such loads per level), and the fold of the two
+// top levels scans all 256 parked entries nine times per warp.
+// Here 8 lanes share a point, lane = child: one 384-byte contiguous block of 8 children per point and level (3 coalesced
+// LDG.128 per lane instead of 24 scattered ones), the arg-max / sum over the 8 children are three xor-shuffles inside the
+// 8-lane group, and 8x more warps are in flight for the same cloud.  Levels 0 and 1 (72 nodes) accumulate with shared-memory
+// fp64 atomics (one flush of the non-zero entries per CTA at the end), deeper levels with global fp64 atomics as before.
+// Semantics are those of reg_estep_kernel / gmmTreeRegESTep (hgmm_gpu.py:550-577): first-maximum arg-max, gamma = 0 when the
+// eight densities sum below 1e-15, stop BEFORE accumulating at a node whose complexity is <= lambda_c, skip gamma < 1e-15.
+// The eight exponentials are summed by a shuffle tree instead of left to right (last-bit differences in gamma).
+__global__ void __launch_bounds__(256) reg_estep2_kernel(const float* __restrict__ tx, const float* __restrict__ ty,
+                                                         const float* __restrict__ tz, int n, const double* __restrict__ Rt,
+                                                         const PackedComp* __restrict__ packed, const float* __restrict__ cplx,
+                                                         int L, float lambda_c, double* __restrict__ racc, int want_m2,
+                                                         const int* __restrict__ ctrl) {
+    if (ctrl[0]) return;
+    __shared__ double s_acc[kTopNodes][kRegMom];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int grp = lane >> 3, c = lane & 7;                    // point slot inside the warp, child
+    const unsigned gmask = 0xffu << (grp * 8);
+    for (int k = tid; k < kTopNodes * kRegMom; k += blockDim.x) (&s_acc[0][0])[k] = 0.0;
+    __syncthreads();
+    const int nm = want_m2 ? kRegMom : 4;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+    for (int base = gwarp * 4; base < n; base += warps_total * 4) {       // warp-uniform trip count
+        const int i = base + grp;
+        bool active = i < n;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (active) {
+            const double a = tx[i], b = ty[i], cc = tz[i];      // t_target = target R^T + t  (hgmm_gpu.py:757,613-614)
+            x = (float)(Rt[0] * a + Rt[1] * b + Rt[2] * cc + Rt[9]);
+            y = (float)(Rt[3] * a + Rt[4] * b + Rt[5] * cc + Rt[10]);
+            z = (float)(Rt[6] * a + Rt[7] * b + Rt[8] * cc + Rt[11]);
+        }
+        int j0 = 0;                                             // child(-1) = 0
+        for (int l = 0; l < L; ++l) {                           // every lane runs all L levels: the shuffles stay convergent
+            float q = kNegBig;
+            if (active) {
+                const float4* c4 = reinterpret_cast<const float4*>(packed + j0 + c);
+                const float4 p0 = __ldg(c4), p1 = __ldg(c4 + 1), p2 = __ldg(c4 + 2);
+                float dx, dy, dz;
+                q = quad_q2(p0, p1, make_float2(p2.x, p2.y), x, y, z, dx, dy, dz);
+            }
+            float m = q;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            m = fmaxf(m, kNegBig);
+            const unsigned hit = __ballot_sync(0xffffffffu, q == m) & gmask;      // first maximum of the group
+            const int best = hit ? (__ffs(hit) - 1 - grp * 8) : 0;
+            float sE = ex2f(q - m);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) sE += __shfl_xor_sync(0xffffffffu, sE, o);
+            const float lse2 = m + lg2f(sE);
+            const bool alive = lse2 > kLog2Eps15;               // den > eps else gamma = zeros (:563-567)
+            const int sid = j0 + (alive ? best : 0);
+            if (active && __ldg(cplx + sid) <= lambda_c) active = false;          // :572-573, before accumulating
+            const float gam = alive ? 1.0f / sE : 0.f;          // gamma of the arg-max child
+            if (active && c == 0 && gam >= 1e-15f) {            // the group's leader accumulates (accumulate() guard :457-459)
+                const double g = gam, X = x, Y = y, Z = z;
+                double v[kRegMom] = {g, g * X, g * Y, g * Z, 0, 0, 0, 0, 0, 0};
+                if (want_m2) {
+                    v[4] = g * X * X; v[5] = g * X * Y; v[6] = g * X * Z; v[7] = g * Y * Y; v[8] = g * Y * Z; v[9] = g * Z * Z;
+                }
+                double* A = sid < kTopNodes ? &s_acc[sid][0] : racc + (size_t)sid * kRegMom;
+#pragma unroll
+                for (int k = 0; k < kRegMom; ++k)
+                    if (k < nm) atomicAdd(A + k, v[k]);
+            }
+            j0 = (sid + 1) * 8;
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < kTopNodes * kRegMom; k += blockDim.x) {
+        const double v = (&s_acc[0][0])[k];
+        if (v != 0.0) atomicAdd(racc + k, v);                   // racc is [node][kRegMom]: same flat index
     }
 }
 
@@ -456,6 +540,16 @@ __global__ void fill_vbo_kernel(const float* __restrict__ x, const float* __rest
 cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, int n, const double* Rt, const TreeModel& t,
                              float lambda_c, double* racc, int want_m2, const int* ctrl, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
+    static const bool v2 = getenv("HGMM_REG_ESTEP2") && getenv("HGMM_REG_ESTEP2")[0] == '1';      // draft switch, see reg_estep2_kernel
+    if (v2) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int need = (n + 31) / 32;                          // CTAs if every warp took exactly one group of 4 points
+        const int grid = need < sms * 8 ? need : sms * 8;
+        reg_estep2_kernel<<<grid, 256, 0, s>>>(tx, ty, tz, n, Rt, t.packed, t.cplx, t.L, lambda_c, racc, want_m2, ctrl);
+        return cudaGetLastError();
+    }
     reg_estep_kernel<<<(n + 255) / 256, 256, 0, s>>>(tx, ty, tz, n, Rt, t.packed, t.cplx, t.L, lambda_c, racc, want_m2, ctrl);
     return cudaGetLastError();
 }

@@ -230,27 +230,17 @@ __device__ __forceinline__ float2 t_fmul2(float2 a, float2 b) {
     return *reinterpret_cast<float2*>(&d);
 }
 
-__global__ void __launch_bounds__(256, 3) tree_estep2_kernel(const float* __restrict__ px, const float* __restrict__ py,
-                                                             const float* __restrict__ pz,
-                                                             const int* __restrict__ chunk_parent,
-                                                             const int* __restrict__ chunk_start,
-                                                             const int* __restrict__ chunk_len,
-                                                             const int* __restrict__ n_chunks_dev,
-                                                             const PackedComp* __restrict__ packed_level,
-                                                             double* __restrict__ acc, uint8_t* __restrict__ slot,
-                                                             const int* __restrict__ done_flag) {
-    // programmatic dependent launch (the build is launch-bound: ~3 us of work per EM iteration): this grid may be scheduled
-    // while the M-step of the previous iteration drains; everything that kernel wrote is read after the wait, from L2
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (__ldcg(done_flag)) return;
-    __shared__ float s_part[8][8 * kMom];
-    __shared__ int s_parent[8];
-    __shared__ double s_ll[8];
+// E-step of the eight chunks [8 * group, 8 * group + 8) by one CTA of 8 warps (the body shared by tree_estep2_kernel and the
+// persistent tree_level_kernel); ends with the CTA-level fold into acc, callers separate consecutive groups with a barrier
+__device__ __forceinline__ void tree_estep2_group(const float* __restrict__ px, const float* __restrict__ py,
+                                                  const float* __restrict__ pz, const int* __restrict__ chunk_parent,
+                                                  const int* __restrict__ chunk_start, const int* __restrict__ chunk_len,
+                                                  int n_chunks, const PackedComp* __restrict__ packed_level,
+                                                  double* __restrict__ acc, uint8_t* __restrict__ slot, int group,
+                                                  float (*s_part)[8 * kMom], int* s_parent, double* s_ll) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cp = lane >> 3, pl = lane & 7;
-    const int chunk = blockIdx.x * 8 + warp;
-    const int n_chunks = __ldcg(n_chunks_dev);
+    const int chunk = group * 8 + warp;
     double ll = 0.0;
     int my_parent = -1;
     if (chunk < n_chunks) {
@@ -366,11 +356,34 @@ __global__ void __launch_bounds__(256, 3) tree_estep2_kernel(const float* __rest
     }
 }
 
+__global__ void __launch_bounds__(256, 3) tree_estep2_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                             const float* __restrict__ pz,
+                                                             const int* __restrict__ chunk_parent,
+                                                             const int* __restrict__ chunk_start,
+                                                             const int* __restrict__ chunk_len,
+                                                             const int* __restrict__ n_chunks_dev,
+                                                             const PackedComp* __restrict__ packed_level,
+                                                             double* __restrict__ acc, uint8_t* __restrict__ slot,
+                                                             const int* __restrict__ done_flag) {
+    // programmatic dependent launch (the build is launch-bound: ~3 us of work per EM iteration): this grid may be scheduled
+    // while the M-step of the previous iteration drains; everything that kernel wrote is read after the wait, from L2
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (__ldcg(done_flag)) return;
+    __shared__ float s_part[8][8 * kMom];
+    __shared__ int s_parent[8];
+    __shared__ double s_ll[8];
+    tree_estep2_group(px, py, pz, chunk_parent, chunk_start, chunk_len, __ldcg(n_chunks_dev), packed_level, acc, slot, blockIdx.x, s_part,
+                      s_parent, s_ll);
+}
+
 // ------------------------------------------------------------------------------------------
 // M-step: one thread per node of the level
 // ------------------------------------------------------------------------------------------
 // done_at[it] is written by iteration it-1 only.  merge_converge != 0 (fast log-likelihood mode): thread 0 of block 0
 // also applies the |q - prevQ| < ls rule to acc[0] (complete: the E-step has finished) and arms done_at[it+1].
+__device__ void tree_mstep_node(const TreeModel& t, int lb, int local, double* __restrict__ acc, double n_total, float ld);
+
 __global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __restrict__ acc, double n_total, float ld,
                                   int* __restrict__ ctrl, int* __restrict__ done_at, int it, int merge_converge,
                                   double* __restrict__ qstate, float ls, int max_iters, volatile int* prog) {
@@ -401,6 +414,11 @@ __global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __rest
     if (done) return;
     const int local = blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= count) return;
+    tree_mstep_node(t, lb, local, acc, n_total, ld);
+}
+
+// moments of node `local` of the level -> parameters (mlEstimator, hgmm_cupy_cpu_working.py:109-119), re-packed; moments cleared
+__device__ void tree_mstep_node(const TreeModel& t, int lb, int local, double* __restrict__ acc, double n_total, float ld) {
     const int j = lb + local;
     double* Ag = acc + kAccHdr + (size_t)local * kMom;
     double A[kMom];
@@ -432,6 +450,69 @@ __global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __rest
     }
 #pragma unroll
     for (int k = 0; k < kMom; ++k) Ag[k] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent level kernel (DRAFT: compiled, not yet run on a GPU -- selected only by HGMM_TREE_PERSIST=1, single rank,
+// HGMM_LL_ESTEP).  The two-kernel iteration costs ~17 us for ~3 us of arithmetic: here one cooperative launch
+// runs the whole EM loop of a level -- E-step over a grid-stride loop of 8-chunk groups, grid barrier, M-step spread over every
+// thread of the grid + the stopping rule by thread 0, grid barrier -- so an iteration costs two grid barriers instead of two
+// launch boundaries and no flag ever travels to the host.
+// gbar: [0] arrival counter, [1] generation.  All CTAs are co-resident (cudaLaunchCooperativeKernel).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned* gbar, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned* vb = gbar;
+        const unsigned gen = vb[1];
+        __threadfence();                                   // this CTA's writes are visible before it counts as arrived
+        if (atomicAdd(gbar, 1u) == nblocks - 1) {
+            vb[0] = 0u;
+            __threadfence();
+            atomicAdd(gbar + 1, 1u);                       // release the generation
+        } else {
+            while (vb[1] == gen) {}
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 3) tree_level_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                            const float* __restrict__ pz, const int* __restrict__ chunk_parent,
+                                                            const int* __restrict__ chunk_start, const int* __restrict__ chunk_len,
+                                                            const int* __restrict__ n_chunks_dev, TreeModel t, int lb, int count,
+                                                            double* __restrict__ acc, uint8_t* __restrict__ slot, double n_total,
+                                                            float ld, float ls, int max_iters, int* __restrict__ ctrl,
+                                                            double* __restrict__ qstate, unsigned* __restrict__ gbar) {
+    __shared__ float s_part[8][8 * kMom];
+    __shared__ int s_parent[8];
+    __shared__ double s_ll[8];
+    const int n_chunks = *n_chunks_dev;
+    const int n_groups = (n_chunks + 7) / 8;
+    const PackedComp* packed_level = t.packed + lb;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    for (int it = 0; it < max_iters; ++it) {
+        for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+            tree_estep2_group(px, py, pz, chunk_parent, chunk_start, chunk_len, n_chunks, packed_level, acc, slot, g, s_part, s_parent,
+                              s_ll);
+            __syncthreads();                               // s_part / s_parent / s_ll are reused by the next group
+        }
+        grid_barrier(gbar, gridDim.x);                     // every moment and the log-likelihood sum have landed in acc
+        if (gtid == 0) {                                   // stopping rule of tree_mstep_kernel (merge_converge branch)
+            const double q = __ldcg(acc);
+            acc[0] = 0.0;
+            const int n_it = it + 1;
+            ctrl[1] = n_it;
+            qstate[1] = q;
+            const bool conv = fabs(q - __ldcg(qstate)) < (double)ls || n_it >= max_iters;
+            qstate[0] = q;
+            ctrl[0] = conv ? 1 : 0;
+        }
+        for (int local = gtid; local < count; local += gthreads) tree_mstep_node(t, lb, local, acc, n_total, ld);
+        grid_barrier(gbar, gridDim.x);                     // new parameters and the verdict are visible everywhere
+        if (__ldcg(ctrl) != 0) break;
+    }
 }
 
 // |q - prevQ| < ls with prevQ = 0 at level start (hgmm_gpu.py:520,533-535).  qstate: [0] prevQ, [1] last q.
@@ -720,6 +801,28 @@ void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_tota
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, tree_mstep_kernel, t, level_base(level), cnt, acc, n_total, ld, ctrl, done_at, it, merge_converge, qstate,
                        ls, max_iters, (volatile int*)prog);
+}
+
+// one cooperative launch for the whole EM loop of a level; returns cudaErrorNotSupported when the device cannot co-schedule
+cudaError_t launch_tree_level(const TreeWork& w, const TreeModel& t, int level, double* acc, int n_chunks_bound,
+                              const int* n_chunks_dev, double n_total, float ld, float ls, int max_iters, int* ctrl, double* qstate,
+                              unsigned* gbar, int num_sms, cudaStream_t s) {
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tree_level_kernel, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorNotSupported;
+    int grid = (n_chunks_bound + 7) / 8;
+    const int cap = occ * num_sms;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    const float *px = w.x, *py = w.y, *pz = w.z;
+    const int *cpar = w.chunk_parent, *cst = w.chunk_start, *cln = w.chunk_len;
+    TreeModel tm = t;
+    int lb = level_base(level), cnt = level_count(level);
+    uint8_t* slot = w.slot;
+    void* args[] = {&px, &py, &pz, &cpar, &cst, &cln, &n_chunks_dev, &tm, &lb, &cnt, &acc, &slot, &n_total, &ld, &ls, &max_iters,
+                    &ctrl, &qstate, &gbar};
+    return cudaLaunchCooperativeKernel((const void*)tree_level_kernel, dim3(grid), dim3(256), args, 0, s);
 }
 
 void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, int* prog,

@@ -1,0 +1,72 @@
+"""Config-size tree fixtures: the float64 oracle (oracle/hgmm_tree.py, pinned to the unmodified reference by
+oracle/make_golden.py) run ONCE on BASELINE.json's synthetic LiDAR workloads.  TEST INFRASTRUCTURE ONLY.
+
+    python -m oracle.make_golden_lidar c3_estep      # 100k-pt sweep (seed 2024), L=4, fast log-likelihood mode   (~1 min)
+    python -m oracle.make_golden_lidar c3_level      # same, the reference's whole-level log-likelihood           (~30 min)
+    python -m oracle.make_golden_lidar c5_50k        # 50k subsample of the 1M-pt sweep (seed 2025), L=5, both modes
+
+The clouds are regenerated from hgmm_b200/synth.py at test time; the fixture stores a checksum of the cloud, the oracle's
+(pi, mu, cov) as float32 (6e-8 relative, far below the 1e-4 parity bar), the per-level iteration counts, the q trace and
+every point's leaf assignment (level-local index, uint16).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gpu-accelerated-point-cloud-registration-using-hierarchical-gmm_b200"))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from oracle import hgmm_tree            # noqa: E402
+from hgmm_b200 import synth             # noqa: E402
+
+C5_SUB = 50000
+
+
+def c3_cloud():
+    return synth.lidar_sweep(100000, seed=2024)
+
+
+def c5_subsample():
+    """the first 50k points of the fixed seeded shuffle (seed 0, the one dist.shuffled_shard applies) of the C5 cloud"""
+    P = synth.lidar_sweep(1000000, seed=2025)
+    perm = np.random.default_rng(0).permutation(len(P))
+    return P[perm[:C5_SUB]]
+
+
+def run(tag, P, L, mode, sig2=4.0, ls=20.0, ld=1e-4):
+    init = P[hgmm_tree.reference_init_indices(L)]
+    t0 = time.time()
+    pi, mu, cov, cur, iters, trace = hgmm_tree.build_gmm_tree(P, L, ls, ld, init.astype(np.float64), sig2=np.float32(sig2),
+                                                             ll_mode=mode, return_trace=True)
+    dt = time.time() - t0
+    print("%s[%s]: %d points, L=%d: iterations %s, %.1f s of oracle time" % (tag, mode, len(P), L, iters, dt), flush=True)
+    lb = hgmm_tree.level(L - 1)
+    np.savez_compressed(os.path.join(GOLD, "tree_build_%s_%s.npz" % (tag, mode)), n=np.int64(len(P)), L=np.int64(L),
+                        ls=np.float64(ls), ld=np.float64(ld), sig2=np.float64(sig2),
+                        cloud_checksum=np.asarray(P, np.float64).sum(axis=0), pi=pi.astype(np.float32), mu=mu.astype(np.float32),
+                        cov=cov.astype(np.float32), iters=np.array(iters, np.int32),
+                        q_last=np.array([[q for (l, _, q) in trace if l == lv][-1] for lv in range(L)]),
+                        current_leaf=(cur - lb).astype(np.uint16), oracle_seconds=np.float64(dt))
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "c3_estep"
+    if what == "c3_estep":
+        run("lidar100k_L4", c3_cloud(), 4, "estep")
+    elif what == "c3_level":
+        run("lidar100k_L4", c3_cloud(), 4, "level")
+    elif what == "c5_50k":
+        P = c5_subsample()
+        run("lidar50k_L5", P, 5, "estep")
+        run("lidar50k_L5", P, 5, "level")
+    else:
+        raise SystemExit("unknown target " + what)
+
+
+if __name__ == "__main__":
+    main()

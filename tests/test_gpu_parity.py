@@ -385,9 +385,16 @@ def test_registration_procrustes_matches_oracle(engine):
     assert rel_fro(rot, oR) < TOL and np.abs(t - ot).max() < 1e-6
     assert abs(q - oq) < 1e-6 * max(abs(oq), 1e-12) + 1e-12
     assert abs(np.linalg.det(rot) - 1.0) < 1e-9 and np.abs(rot @ rot.T - np.identity(3)).max() < 1e-9
+    # the whole loop against the oracle's loop (same solver), ONE direction: the engine returns the forward transform
+    # (target -> model), the oracle / reference its inverse (hgmm_gpu.py:768)
     rot, t, q, it, _ = engine.register_tree(solver="procrustes_svd", maxiter=30, tol=1e-9)
-    inv = rot.T
-    assert rel_fro(inv, g["true_rot"].T) < 5e-2 or rel_fro(rot, g["true_rot"].T) < 5e-2
+    lR, lt, lq, lit = oreg.registration(g["target"], g["pi"].astype(np.float64), g["mu"].astype(np.float32).astype(np.float64),
+                                        g["cov"].astype(np.float32).astype(np.float64), L, float(g["lambda_c"]), 30, 1e-9,
+                                        solver="procrustes")
+    assert rel_fro(np.c_[rot.T, -rot.T @ t], np.c_[lR, lt]) < 10 * TOL, (rel_fro(rot.T, lR), it, lit)
+    assert abs(it - lit) <= 1
+    # target = true_rot . source + t0, so the forward rotation is true_rot^T (8 degrees about z): direction check
+    assert rel_fro(rot, g["true_rot"].T) < 5e-2 and rel_fro(rot, g["true_rot"]) > 0.1      # oracle: 3.9e-2 / 0.19
 
 
 def test_bunny_registration_matches_oracle_on_real_scans(engine, bun000, bun045):
