@@ -1,13 +1,20 @@
-"""bench.py -- EM throughput of the flat J=800 fit on bun000 (BASELINE.json configs[1]) on N B200s.
+"""bench.py -- the hierarchical-GMM fit / register hot path on N B200s (BASELINE.json).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W    # CPU reference arm (the oracle's C port, all host threads)
 
-A "step" is ONE fit: 10 EM iterations (the reference's solve(..., 10, ...), gmm_kernels.cu:588) of the
-full-covariance J=800 mixture over the 40 256-point cloud (per rank: weak scaling, every rank owns a
-same-size shard and the O(J) sufficient statistics are all-reduced every iteration).
-value  = points x EM-iterations processed by all ranks per second, cloud resident in HBM.
-e2e    = the same through the public API with HOST buffers (H2D of the cloud + init, D2H of the model each step).
+Headline (`metric`, `value`, `e2e`, `roofline`, `cpu_baseline`): configs[1], the flat full-covariance J=800 fit of bun000.
+A "step" is ONE fit: 10 EM iterations (the reference's solve(..., 10, ...), gmm_kernels.cu:588) over the 40 256-point cloud
+(per rank: weak scaling, every rank owns a same-size shard and the O(J) sufficient statistics are exchanged every iteration).
+value = points x EM-iterations processed by all ranks per second, cloud resident in HBM.
+e2e   = the same through the public API with HOST buffers (H2D of the cloud + init, D2H of the model each step).
+
+Beside it, on the same line (each with its own roofline / cpu_baseline / e2e blocks):
+  "c3": configs[2]  HGMM depth 4 on the 100k-point synthetic LiDAR sweep                      (N = 1)
+  "c4": configs[3]  registration bun000 -> bun045, flat J=100 fit + weighted-Procrustes solve  (N = 1)
+  "c5": configs[4]  1M-point synthetic LiDAR, HGMM depth 5, points sharded over the N ranks (STRONG scaling: the cloud is
+        fixed), next to the same build on ONE GPU of the same box and their parity
+  "parity_vs_single" (N > 1): sharded fits against a single-GPU engine on rank 0; the process exits non-zero above 1e-4.
 Prints one JSON line on rank 0.
 """
 import argparse
@@ -31,22 +38,32 @@ EM_ITERS = 10
 SIGMA0_SQ = 1e-4
 METRIC = "flat GMM EM throughput, J=800 full-cov on bun000 (EM iters/s x N pts)"
 UNIT = "Mpoint-iters/s"
+PARITY_TOL = 1e-4
 
 
 def load_cloud():
     path = os.path.join(ROOT, "tests", "golden", "bun000_xyz.npy")
     if os.path.exists(path):
         return np.load(path).astype(np.float32), "bun000.ply vertices (40256 pts, committed fixture)"
-    from oracle import synth
+    from hgmm_b200 import synth
     return synth.bunny_like(40256, seed=0), "synthetic bunny-like surface (40256 pts)"
 
 
-def init_model(X, seed=1):
+def init_model(X, seed=1, j=J, s0=SIGMA0_SQ):
     rng = np.random.default_rng(seed)
-    mu0 = X[rng.choice(len(X), J, replace=False)].astype(np.float32)
-    cov0 = np.tile(np.eye(3, dtype=np.float32) * np.float32(SIGMA0_SQ), (J, 1, 1))
-    w0 = np.full(J, 1.0 / J, np.float32)
+    mu0 = X[rng.choice(len(X), j, replace=False)].astype(np.float32)
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * np.float32(s0), (j, 1, 1))
+    w0 = np.full(j, 1.0 / j, np.float32)
     return mu0, cov0, w0
+
+
+def workload_config(n, world):
+    """identical in both arms (the driver compares the dicts)"""
+    return {"workload": "configs[1]: flat GMM J=800 full-cov on bun000, 10 EM iterations per step",
+            "points_per_gpu": int(n), "components": J, "em_iters_per_step": EM_ITERS, "init": "seeded points, Sigma0=1e-4*I",
+            "l2": "256 MiB buffer written between steps (the 10 sweeps inside a step re-read the 483 kB cloud as the algorithm does)",
+            "parallelism": "dp%d: points sharded; per EM iteration the J*10 fp64 moments are exchanged inside the M-step kernel by NVLink "
+                           "stores into peer memory (ncclAllReduce when the ranks cannot map each other)" % world}
 
 
 def measured_peaks():
@@ -58,6 +75,32 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def rel_fro(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def lidar(n, seed):
+    """the synthetic 64-beam sweep of SURVEY.md 8d, cached per box (the 1M-point cloud takes ~25 s of ray casting)"""
+    from hgmm_b200 import synth
+    cache = "/tmp/hgmm_lidar_%d_%d.npy" % (n, seed)
+    if os.path.exists(cache):
+        try:
+            P = np.load(cache)
+            if P.shape == (n, 3):
+                return P
+        except Exception:
+            pass
+    P = synth.lidar_sweep(n, seed=seed)
+    try:
+        np.save(cache + ".%d.tmp.npy" % os.getpid(), P)
+        os.replace(cache + ".%d.tmp.npy" % os.getpid(), cache)
+    except Exception:
+        pass
+    return P
 
 
 class ClockSampler:
@@ -109,16 +152,8 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def run_reference(args):
-    """CPU arm: the oracle's plain-C/OpenMP port of the same fit on all host threads (the reference has no CPU
-    implementation of its full-covariance fitter; its CUDA binary is timed separately, see DESIGN.md)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import c_oracle
-    X, src = load_cloud()
-    mu0, _, _ = init_model(X)
-    # use whichever of {all logical CPUs, half of them (one per physical core)} runs the fit faster
+def c_port_threads(c_oracle, X, mu0):
+    """whichever of {all logical CPUs, half of them (one per physical core)} runs the fit faster"""
     best = None
     for nt in sorted({os.cpu_count() or 1, max(1, (os.cpu_count() or 2) // 2)}):
         c_oracle.set_threads(nt)
@@ -129,7 +164,19 @@ def run_reference(args):
         if best is None or dt < best[0]:
             best = (dt, nt)
     c_oracle.set_threads(best[1])
-    cores = best[1]
+    return best[1]
+
+
+def run_reference(args):
+    """CPU arm: the oracle's plain-C/OpenMP port of the same fit on all host threads (the reference has no CPU
+    implementation of its full-covariance fitter; its CUDA binary is timed separately, see DESIGN.md)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    X, src = load_cloud()
+    mu0, _, _ = init_model(X)
+    cores = c_port_threads(c_oracle, X, mu0)
     for _ in range(max(args.warmup, 1)):
         c_oracle.flat_fit(X, mu0, 1, SIGMA0_SQ)
     t0 = time.perf_counter()
@@ -137,15 +184,13 @@ def run_reference(args):
         c_oracle.flat_fit(X, mu0, EM_ITERS, SIGMA0_SQ)
     dt = time.perf_counter() - t0
     val = len(X) * EM_ITERS * args.steps / dt / 1e6
-    sample = "full workload: %d steps x %d EM iterations x %d pts x J=%d" % (args.steps, EM_ITERS, len(X), J)
+    sample = "full workload: %d steps x %d EM iterations x %d pts x J=%d, fp64, OpenMP, %d threads" % (args.steps, EM_ITERS, len(X), J, cores)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f64", "data": src,
-           "config": {"workload": "configs[1]: flat GMM J=800 full-cov on bun000, 10 EM iterations per step", "points": int(len(X)),
-                      "components": J, "em_iters_per_step": EM_ITERS},
+           "vs_baseline": None, "dtype": "f64", "data": src, "config": workload_config(len(X), args.gpus),
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "em_iters_per_sec": EM_ITERS * args.steps / dt}
+           "em_iters_per_sec": EM_ITERS * args.steps / dt, "cpu_threads": cores}
     print(json.dumps(out))
 
 
@@ -155,7 +200,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own")
-    ap.add_argument("--extras", type=int, default=1, help="also time the tree / registration workloads (rank 0, N=1, untimed region)")
+    ap.add_argument("--extras", type=int, default=1, help="also run the configs[2..4] legs and, at N > 1, the sharded-vs-single parity")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -189,8 +234,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ------------------------------------------------------------ device-resident throughput (value)
-    eng.set_points(torch.from_numpy(X).cuda())
+    eng.set_points(torch.from_numpy(X).cuda(), total=n * world)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -215,35 +266,28 @@ def main():
         ev[k][1].record(stream)
     barrier()
     launches = eng.launch_count - launches0
-    t_ms = sum(a.elapsed_time(b) for a, b in ev)
-    tt = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_ms = float(tt.item())
+    t_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
     total_pts = n * world
     value = total_pts * EM_ITERS * args.steps / (t_ms * 1e-3) / 1e6
 
     # ------------------------------------------------------------ end to end through the public API, host buffers
     Xpin = torch.from_numpy(X).pin_memory()
     for _ in range(2):
-        eng.set_points(Xpin)
+        eng.set_points(Xpin, total=n * world)
         eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=EM_ITERS)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        eng.set_points(Xpin)                                                     # H2D of the step's cloud
+        eng.set_points(Xpin, total=n * world)                                    # H2D of the step's cloud
         res = eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=EM_ITERS)    # H2D init, D2H fitted model + log-lik
     barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = total_pts * EM_ITERS * args.steps / float(te.item()) / 1e6
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_val = total_pts * EM_ITERS * args.steps / e2e_s / 1e6
     h2d = n * 12 + J * (3 + 9 + 1) * 4
     d2h = J * (3 + 9 + 1) * 4 + EM_ITERS * 8 + 8 * 4
 
     # ------------------------------------------------------------ per-kernel roofline (separate, profiled pass)
-    eng.set_points(torch.from_numpy(X).cuda())
+    eng.set_points(torch.from_numpy(X).cuda(), total=n * world)
     eng.set_profiling(True)
     k_ms, k_cnt = 0.0, 0
     for _ in range(5):
@@ -260,39 +304,33 @@ def main():
     flops_alg = 52.0 * n * J                         # 52 flop per (point, component) pair
     hbm_peak, hbm_src = measured_peaks()
     peak_imm, peak_reg, peak_packed = eng.measure_fp32_peak()
-    fp32_peak = peak_packed
+    sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    nominal_fp32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12          # 148 SMs x 128 FMA lanes x 2 flop at the max SM clock
     roof = {"bound": "hbm", "kernel": "em_flat7_kernel", "achieved": bytes_alg / k_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": bytes_alg / k_avg_s / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
             "avg_launch_us": k_avg_s * 1e6,
             "note": "J=800 makes this sweep FP32-issue bound (52*J/12 = 3467 flop/B >> the ~10 flop/B ridge); see roofline_fp32"}
-    roof32 = {"bound": "fp32", "kernel": "em_flat7_kernel", "achieved": flops_alg / k_avg_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-              "frac": flops_alg / k_avg_s / 1e12 / fp32_peak if fp32_peak > 0 else None,
+    roof32 = {"bound": "fp32", "kernel": "em_flat7_kernel", "achieved": flops_alg / k_avg_s / 1e12, "peak": peak_packed, "unit": "TFLOP/s",
+              "frac": flops_alg / k_avg_s / 1e12 / peak_packed if peak_packed > 0 else None,
+              "peak_nominal": nominal_fp32, "frac_of_nominal": flops_alg / k_avg_s / 1e12 / nominal_fp32,
               "peak_source": "measured live: packed FFMA2 register loop (hgmm_measure_fp32_peak); scalar 3-register FFMA measures "
-                             "%.1f, immediate-operand FFMA %.1f TFLOP/s on the same device" % (peak_reg, peak_imm)}
+                             "%.1f, immediate-operand FFMA %.1f TFLOP/s on the same device; nominal = 148 SM x 128 lanes x 2 x %.0f MHz"
+                             % (peak_reg, peak_imm, sm_mhz)}
     prof_json = os.path.join(ROOT, "profiles", "em_flat_traffic.json")
     if os.path.exists(prof_json):
         try:
             roof["traffic"] = json.load(open(prof_json)).get("dram_bytes_per_launch")
+            roof["traffic_source"] = "from profiles/em_flat_traffic.json (one `ncu --set full` capture), not measured in this run"
         except Exception:
             pass
 
-    # ------------------------------------------------------------ CPU baseline (rank 0, N=1) + other workloads
+    # ------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None
-    extras = {}
+    legs = {}
     if rank == 0 and world == 1:
         try:
             from oracle import c_oracle
-            best = None
-            for nt in sorted({os.cpu_count() or 1, max(1, (os.cpu_count() or 2) // 2)}):
-                c_oracle.set_threads(nt)
-                c_oracle.flat_fit(X, mu0, 1, SIGMA0_SQ)
-                t0 = time.perf_counter()
-                c_oracle.flat_fit(X, mu0, 2, SIGMA0_SQ)
-                dtt = time.perf_counter() - t0
-                if best is None or dtt < best[0]:
-                    best = (dtt, nt)
-            cores = best[1]
-            c_oracle.set_threads(cores)
+            cores = c_port_threads(c_oracle, X, mu0)
             t0 = time.perf_counter()
             reps = 0
             while time.perf_counter() - t0 < 10.0 and reps < 8:
@@ -300,72 +338,347 @@ def main():
                 reps += 1
             dt = time.perf_counter() - t0
             cpu = {"value": n * EM_ITERS * reps / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "%d full fits (10 EM iterations, %d pts, J=%d) of oracle/c/em_oracle.c, fp64, OpenMP" % (reps, n, J)}
+                   "sample": "%d full fits (10 EM iterations, %d pts, J=%d) of oracle/c/em_oracle.c, fp64, OpenMP, %d threads" % (reps, n, J, cores)}
         except Exception as e:      # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
-        if args.extras:
+    # ------------------------------------------------------------ the other BASELINE configs
+    parity = None
+    if args.extras:
+        if rank == 0 and world == 1:
+            for name, fn in (("c3", leg_c3), ("c4", leg_c4)):
+                try:
+                    legs[name] = fn(eng, hbm_peak, peak_packed)
+                except Exception as e:
+                    legs[name] = {"error": repr(e)}
+        try:
+            legs["c5"] = leg_c5(eng, world, rank, local, hbm_peak, peak_packed, barrier, max_over_ranks)
+        except Exception as e:
+            legs["c5"] = {"error": repr(e)}
+        if world > 1:
             try:
-                extras = other_workloads(eng, stream)
+                parity = parity_vs_single(eng, world, rank, local)
             except Exception as e:
-                extras = {"error": repr(e)}
+                parity = {"error": repr(e), "ok": False}
+        ref_py = os.path.join(ROOT, "profiles", "r02_reference_python_cpu.json")
+        if rank == 0 and os.path.exists(ref_py):
+            try:
+                legs["reference_python_cpu"] = json.load(open(ref_py))
+            except Exception:
+                pass
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-               "data": src,
-               "config": {"workload": "configs[1]: flat GMM J=800 full-cov on bun000, 10 EM iterations per step",
-                          "points_per_gpu": n, "components": J, "em_iters_per_step": EM_ITERS, "init": "seeded points, Sigma0=1e-4*I",
-                          "l2": "256 MiB buffer written between steps (the 10 sweeps inside a step re-read the 483 kB cloud as the algorithm does)",
-                          "parallelism": ("dp%d: points sharded; per EM iteration the J*10 fp64 moments are exchanged " % world) +
-                                         ("inside the M-step kernel by NVLink stores into peer memory (no NCCL call)" if eng.p2p_enabled
-                                          else "by one fp64 ncclAllReduce" if world > 1 else "(single rank: no exchange)")},
+               "data": src, "config": workload_config(n, world),
+               "exchange": ("peer-memory stores fused into the M-step kernel (no NCCL call)" if eng.p2p_enabled
+                            else "ncclAllReduce (fp64)" if world > 1 else "single rank: none"),
                "em_iters_per_sec": EM_ITERS * args.steps / (t_ms * 1e-3),
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "ms_per_step": float(te.item()) / args.steps * 1e3, "timing": "wall clock, barrier+synchronize on both sides"},
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_fp32": roof32, "cpu_baseline": cpu,
-               "other_workloads": extras}
+                       "ms_per_step": e2e_s / args.steps * 1e3, "timing": "wall clock, barrier+synchronize on both sides"},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_fp32": roof32, "cpu_baseline": cpu}
+        out.update(legs)
+        if parity is not None:
+            out["parity_vs_single"] = parity
         print(json.dumps(out))
+    bad = parity is not None and not parity.get("ok", False)
     if world > 1:
+        flag = torch.tensor([1 if bad else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        bad = int(flag.item()) != 0
         eng.comm_destroy()
         dist.destroy_process_group()
+    if bad:
+        sys.exit(3)
 
 
-def other_workloads(eng, stream):
-    """configs[2] and configs[3] timed once each on the device (CUDA events via the library), for context."""
+# ------------------------------------------------------------------------------------------------------------------
+# algorithmic traffic of a tree build: per level iters_l (16 N + 104 8^(l+1)) bytes, 52 * 8 * N flop;
+# per level hand-off one partition pass of 2 (8 + 12) N bytes
+def tree_alg(n, iters, with_level_ll=False):
+    byt = sum(it * (16.0 * n + 104.0 * 8 ** (l + 1)) for l, it in enumerate(iters)) + (len(iters) - 1) * 2.0 * (8 + 12) * n
+    flo = sum(it * 52.0 * 8 * n for it in iters)
+    if with_level_ll:
+        flo += sum(it * 34.0 * n * 8 ** (l + 1) for l, it in enumerate(iters))
+    return byt, flo
+
+
+def leg_c3(eng, hbm_peak, fp32_peak):
+    """configs[2]: HGMM depth 4 (4096 leaves) on the 100k-point synthetic LiDAR sweep, 1 GPU"""
     import torch
-    from oracle import synth
     from hgmm_b200 import hgmm as H
-    out = {}
-    # configs[2]: HGMM depth 4 on a 100k-point synthetic LiDAR sweep
-    P = synth.lidar_sweep(100000, seed=2024)
-    init = P[H.reference_init_indices(4)]
+    P = lidar(100000, 2024)
+    L = 4
+    init = P[H.reference_init_indices(L)]
+    out = {"workload": "configs[2]: HGMM 8-ary tree depth 4 on a 100k-point synthetic LiDAR sweep (seed 2024), ls=20, ld=1e-4, sig2=4"}
     eng.set_points(torch.from_numpy(P).cuda())
     for mode in ("estep", "level"):
-        eng.fit_tree(init, 4, ls=20.0, ld=1e-4, sig2=4.0, ll_mode=mode, want_current=False, want_outputs=False)
-        r = eng.fit_tree(init, 4, ls=20.0, ld=1e-4, sig2=4.0, ll_mode=mode, want_current=False, want_outputs=False)
-        ms = float(eng.last_timing_ms()[0])
-        its = int(r["iters"].sum())
-        out["tree_L4_100k_lidar_ll_%s" % mode] = {"build_ms": ms, "em_iterations": its, "iters_per_level": r["iters"].tolist(),
-                                                  "em_iters_per_sec": its / (ms * 1e-3)}
-    # configs[3]: registration bun000 -> bun045 against a depth-3 tree (fit + <=20 iterations)
+        reps = 4 if mode == "estep" else 2
+        ms = []
+        for _ in range(reps):
+            r = eng.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4.0, ll_mode=mode, want_current=False, want_outputs=False)
+            ms.append(float(eng.last_timing_ms()[0]))
+        best = min(ms[1:])
+        its = r["iters"].tolist()
+        byt, flo = tree_alg(len(P), its, mode == "level")
+        out["ll_" + mode] = {"build_ms": best, "em_iterations": int(sum(its)), "iters_per_level": its,
+                             "em_iters_per_sec": sum(its) / (best * 1e-3), "us_per_em_iteration": best * 1e3 / max(sum(its), 1),
+                             "mpoint_iters_per_sec": len(P) * sum(its) / (best * 1e-3) / 1e6,
+                             "roofline": {"bound": "hbm", "kernel": "tree_level_kernel" if mode == "estep" else "tree_estep2 + scan_components",
+                                          "achieved": byt / (best * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                          "frac": byt / (best * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                                          "alg_bytes": byt, "note": "whole build / device time of the build (CUDA events on the library stream)"},
+                             "roofline_fp32": {"bound": "fp32", "achieved": flo / (best * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                                               "frac": flo / (best * 1e-3) / 1e12 / fp32_peak if fp32_peak else None}}
+    # e2e: host cloud in, model out, wall clock
+    Ppin = torch.from_numpy(P).pin_memory()
+    t_best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        eng.set_points(Ppin)
+        r = eng.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4.0, ll_mode="estep", want_current=True)
+        dt = time.perf_counter() - t0
+        t_best = dt if t_best is None or dt < t_best else t_best
+    its = int(r["iters"].sum())
+    out["e2e"] = {"value": len(P) * its / t_best / 1e6, "unit": "Mpoint-iters/s", "builds_per_sec": 1.0 / t_best, "ms_per_build": t_best * 1e3,
+                  "h2d_bytes_per_step": len(P) * 12 + 4680 * 12, "d2h_bytes_per_step": 4680 * 52 + len(P) * 8,
+                  "timing": "wall clock around set_points(host) + fit_tree(ll_mode=estep) incl. the leaf assignment of every point"}
+    # CPU: the float64 vectorised oracle (the reference's own tree build is a per-point pure-Python loop: see reference_python_cpu)
+    try:
+        from oracle import hgmm_tree
+        sub = P[:20000]
+        i3 = sub[hgmm_tree.reference_init_indices(3)]
+        t0 = time.perf_counter()
+        _, _, _, _, oit, _ = hgmm_tree.build_gmm_tree(sub, 3, 20.0, 1e-4, i3.astype(np.float64), sig2=np.float32(4.0), ll_mode="estep",
+                                                      return_trace=True, max_iters_per_level=40)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": len(sub) * sum(oit) / dt / 1e6, "unit": "Mpoint-iters/s", "cores": 1, "kind": "port",
+                               "sample": "oracle/hgmm_tree.py (NumPy float64) on the first 20k points, depth 3, %d EM iterations in %.1f s" % (sum(oit), dt)}
+    except Exception as e:
+        out["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
+    return out
+
+
+def bunny_pose():
+    """data/bun.conf:3 -- p_bun000frame = Rq^T p_bun045 + tq"""
+    x, y, z, w = 0.00548449, -0.294635, -0.0038555, 0.955586
+    Rq = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                   [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                   [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return Rq, np.array([-0.0520211, -0.000383981, -0.0109223])
+
+
+def leg_c4(eng, hbm_peak, fp32_peak):
+    """configs[3]: registration bun000 -> bun045, flat J=100 fit + weighted-Procrustes SE(3) solve, 1 GPU"""
+    import torch
+    from hgmm_b200 import hgmm as H
     b0 = os.path.join(ROOT, "tests", "golden", "bun000_xyz.npy")
     b45 = os.path.join(ROOT, "tests", "golden", "bun045_xyz.npy")
-    if os.path.exists(b0) and os.path.exists(b45):
-        S, T = np.load(b0), np.load(b45)
-        init = S[H.reference_init_indices(3)]
-        eng.set_points(torch.from_numpy(S).cuda())
-        eng.reg_set_target(torch.from_numpy(T).cuda())
-        for _ in range(2):
-            t0 = time.perf_counter()
-            eng.fit_tree(init, 3, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False, want_outputs=False)
-            fit_ms = float(eng.last_timing_ms()[0])
-            rot, t, q, it, _ = eng.register_tree(solver="twist_lstsq", maxiter=20, tol=1e-4)
-            reg_ms = float(eng.last_timing_ms()[0])
-            torch.cuda.synchronize()
-            wall = time.perf_counter() - t0
-        out["registration_bun000_bun045_L3"] = {"tree_fit_ms": fit_ms, "register_ms": reg_ms, "iterations": it,
-                                                "fps_device": 1e3 / (fit_ms + reg_ms), "fps_wall": 1.0 / wall}
+    if not (os.path.exists(b0) and os.path.exists(b45)):
+        return {"error": "bunny fixtures missing"}
+    S, T = np.load(b0), np.load(b45)
+    Jc = 100
+    mu0, cov0, w0 = init_model(S, seed=12, j=Jc)
+    Rq, tq = bunny_pose()
+    out = {"workload": "configs[3]: bun000 (40256 pts) -> bun045 (40097 pts), flat J=100 full-cov fit (10 EM iterations) + weighted-Procrustes "
+                       "registration (<= 20 iterations, tol 1e-4)"}
+    Spin, Tpin = torch.from_numpy(S).pin_memory(), torch.from_numpy(T).pin_memory()
+    frames = []
+    for k in range(6):
+        t0 = time.perf_counter()
+        eng.set_points(Spin)
+        eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False)
+        fit_ms = float(eng.last_timing_ms()[0])
+        eng.reg_set_target(Tpin)
+        rot, t, q, it, _ = eng.register_flat(solver="procrustes_svd", maxiter=20, tol=1e-4)
+        reg_ms = float(eng.last_timing_ms()[0])
+        frames.append((time.perf_counter() - t0, fit_ms, reg_ms, it))
+    wall, fit_ms, reg_ms, it = min(frames[1:])
+    ang = float(np.rad2deg(np.arccos(np.clip((np.trace(rot @ Rq) - 1) / 2, -1, 1))))
+    per_it = reg_ms / max(it, 1) * 1e-3
+    byt = 36.0 * len(T) + 104.0 * Jc            # target read + transformed copy written + read by the sweep, + the mixture
+    out["flat_J100_procrustes"] = {
+        "fit_ms": fit_ms, "register_ms": reg_ms, "iterations": int(it), "fps_device": 1e3 / (fit_ms + reg_ms),
+        "angle_to_bun_conf_deg": ang, "translation": [float(v) for v in t], "q": float(q),
+        "note": "soft responsibilities over all 100 components with no outlier term on partial-overlap scans: the pose error is the "
+                "algorithm's (the float64 oracle lands on the same transform, tests/test_gpu_parity.py), not the kernels'",
+        "roofline": {"bound": "hbm", "kernel": "transform_soa + em_flat3 sweep + reduce + solve (one registration iteration)",
+                     "achieved": byt / per_it / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byt / per_it / 1e9 / hbm_peak, "traffic": None},
+        "roofline_fp32": {"bound": "fp32", "achieved": 52.0 * len(T) * Jc / per_it / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                          "frac": 52.0 * len(T) * Jc / per_it / 1e12 / fp32_peak if fp32_peak else None}}
+    out["e2e"] = {"value": 1.0 / wall, "unit": "registrations/s (fps)", "ms_per_frame": wall * 1e3,
+                  "h2d_bytes_per_step": (len(S) + len(T)) * 12 + Jc * 13 * 4, "d2h_bytes_per_step": 12 * 8 + 20 * 8,
+                  "timing": "wall clock around set_points(host) + fit_flat + reg_set_target(host) + register_flat"}
+    # the hierarchical variant of the same registration (src/python/hgmm: depth-3 tree + linearised twist solve)
+    init = S[H.reference_init_indices(3)]
+    eng.set_points(torch.from_numpy(S).cuda())
+    eng.reg_set_target(torch.from_numpy(T).cuda())
+    for _ in range(2):
+        eng.fit_tree(init, 3, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False, want_outputs=False)
+        tfit = float(eng.last_timing_ms()[0])
+        rot3, t3, q3, it3, _ = eng.register_tree(solver="twist_lstsq", maxiter=20, tol=1e-4)
+        treg = float(eng.last_timing_ms()[0])
+    out["tree_L3_twist"] = {"tree_fit_ms": tfit, "register_ms": treg, "iterations": int(it3), "fps_device": 1e3 / (tfit + treg),
+                            "angle_to_bun_conf_deg": float(np.rad2deg(np.arccos(np.clip((np.trace(rot3 @ Rq) - 1) / 2, -1, 1))))}
+    try:
+        from oracle import registration as oreg
+        sub = T[::8]
+        fit = eng.set_points(Spin).fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10)
+        t0 = time.perf_counter()
+        _, _, _, oit = oreg.flat_registration(sub, fit["weights"], fit["means"], fit["covs"], 10, 1e-4, solver="procrustes")
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": len(sub) * oit / dt / 1e6, "unit": "M target-point-iterations/s", "cores": 1, "kind": "port",
+                               "gpu_same_unit": len(T) * it / (reg_ms * 1e-3) / 1e6,
+                               "sample": "oracle/registration.py::flat_registration (NumPy float64) on every 8th target point, %d iterations in %.1f s" % (oit, dt)}
+    except Exception as e:
+        out["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
     return out
+
+
+def leg_c5(eng, world, rank, local, hbm_peak, fp32_peak, barrier, max_over_ranks):
+    """configs[4]: 1M-point synthetic LiDAR (seed 2025), HGMM depth 5, points sharded over the ranks (contiguous shards of the
+    fixed seeded shuffle), the level's sufficient statistics exchanged inside the persistent level kernel.  STRONG scaling."""
+    import torch
+    import torch.distributed as dist
+    import hgmm_b200
+    from hgmm_b200 import dist as hdist, hgmm as H
+    N5, L = 1000000, 5
+    if rank == 0:
+        P = lidar(N5, 2025)
+    barrier()
+    if rank != 0:
+        P = lidar(N5, 2025)
+    init = P[H.reference_init_indices(L)]              # global indices: identical on every rank
+    shard = hdist.shuffled_shard(P, rank, world, seed=0)
+    out = {"workload": "configs[4]: 1M-point synthetic LiDAR sweep (seed 2025), HGMM depth 5 (37448 nodes, 32768 leaves), ls=20, ld=1e-4, "
+                       "sig2=4; seeded shuffle, contiguous shards of %d points per rank" % len(shard),
+           "scaling": "strong", "n_gpus": world, "points_total": N5,
+           "exchange": ("reduce-scatter + all-gather of the level's statistics over peer memory inside tree_level_kernel (no NCCL call)"
+                        if (world > 1 and eng.p2p_enabled) else "ncclAllReduce per EM iteration" if world > 1 else "single rank: none")}
+    eng.set_points(torch.from_numpy(shard).cuda(), total=N5)
+    kw = dict(ls=20.0, ld=1e-4, sig2=4.0, want_current=False, want_outputs=False)
+    for mode, reps in (("estep", 4), ("level", 1)):
+        ms = []
+        for _ in range(reps):
+            barrier()
+            r = eng.fit_tree(init, L, ll_mode=mode, **kw)
+            ms.append(max_over_ranks(float(eng.last_timing_ms()[0])))
+        best = min(ms[1:]) if len(ms) > 1 else ms[0]
+        its = r["iters"].tolist()
+        byt, flo = tree_alg(N5, its, mode == "level")
+        out["ll_" + mode] = {"build_ms": best, "em_iterations": int(sum(its)), "iters_per_level": its,
+                             "em_iters_per_sec": sum(its) / (best * 1e-3), "us_per_em_iteration": best * 1e3 / max(sum(its), 1),
+                             "mpoint_iters_per_sec": N5 * sum(its) / (best * 1e-3) / 1e6,
+                             "roofline": {"bound": "hbm", "achieved": byt / (best * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
+                                          "frac": byt / (best * 1e-3) / 1e9 / (hbm_peak * world), "traffic": None, "alg_bytes": byt,
+                                          "note": "all ranks' algorithmic bytes / max-over-ranks device time; peak = N x the measured HBM figure"},
+                             "roofline_fp32": {"bound": "fp32", "achieved": flo / (best * 1e-3) / 1e12, "peak": fp32_peak * world, "unit": "TFLOP/s",
+                                               "frac": flo / (best * 1e-3) / 1e12 / (fp32_peak * world) if fp32_peak else None}}
+    # e2e: host shard in, model out
+    Spin = torch.from_numpy(shard).pin_memory()
+    walls = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        eng.set_points(Spin, total=N5)
+        r = eng.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4.0, ll_mode="estep", want_current=False)
+        torch.cuda.synchronize()
+        walls.append(max_over_ranks(time.perf_counter() - t0))
+    wall = min(walls[1:])
+    out["e2e"] = {"value": N5 * int(r["iters"].sum()) / wall / 1e6, "unit": "Mpoint-iters/s", "builds_per_sec": 1.0 / wall, "ms_per_build": wall * 1e3,
+                  "h2d_bytes_per_step": len(shard) * 12 + 37448 * 12, "d2h_bytes_per_step": 37448 * 52,
+                  "timing": "wall clock (max over ranks) around set_points(host shard) + fit_tree(ll_mode=estep) + model download"}
+    # the same build on ONE GPU of this box (rank 0, outside every timed region): strong-scaling reference + parity
+    if world > 1:
+        single = None
+        if rank == 0:
+            ref = hgmm_b200.Engine(local)
+            ref.set_points(torch.from_numpy(P).cuda())
+            ms1 = []
+            for _ in range(3):
+                r1 = ref.fit_tree(init, L, ll_mode="estep", **kw)
+                ms1.append(float(ref.last_timing_ms()[0]))
+            single = {"build_ms": min(ms1[1:]), "iters_per_level": r1["iters"].tolist()}
+        # parity at a FIXED iteration count (the stopping rule's crossing iteration depends on the last bits of q at this size)
+        fix = dict(ls=0.0, ld=1e-4, sig2=4.0, ll_mode="estep", max_iters_per_level=8, want_current=False)
+        rs = eng.fit_tree(init, L, **fix)
+        if rank == 0:
+            r1 = ref.fit_tree(init, L, **fix)
+            errs = {k: rel_fro(rs[k], r1[k]) for k in ("pi", "mu", "cov")}
+            single["parity_fixed_8_iters_per_level"] = errs
+            single["parity_ok"] = bool(max(errs.values()) < PARITY_TOL and rs["iters"].tolist() == r1["iters"].tolist())
+            single["strong_scaling_speedup"] = single["build_ms"] / out["ll_estep"]["build_ms"] * \
+                (out["ll_estep"]["em_iterations"] / max(sum(single["iters_per_level"]), 1))
+            single["strong_scaling_efficiency"] = single["strong_scaling_speedup"] / world
+            single["note"] = "speed-up per EM iteration (us/iteration on 1 GPU / us/iteration on N): the iteration COUNT to convergence varies by run"
+            ref.close()
+        out["single_gpu_same_box"] = single
+    else:
+        out["single_gpu_same_box"] = None
+    return out
+
+
+def parity_vs_single(eng, world, rank, local):
+    """N > 1, outside every timed region: sharded fits against a single-GPU engine on rank 0 (flat over peer memory, flat over
+    NCCL, tree in both log-likelihood modes, tree registration, flat registration)."""
+    import torch
+    import torch.distributed as dist
+    import hgmm_b200
+    from hgmm_b200 import dist as hdist, hgmm as H
+    X = np.load(os.path.join(ROOT, "tests", "golden", "bun000_xyz.npy"))[::2]
+    shard = hdist.shuffled_shard(X, rank, world, seed=5)
+    eng.set_points(shard, total=len(X))
+    J8 = 800
+    mu8, cov8, w8 = init_model(X, seed=3, j=J8)
+    p2p_on = eng.p2p_enabled
+    f_p2p = eng.fit_flat(mu8, cov8, w8, cov_type="full", max_iter=8)
+    if p2p_on:
+        eng.p2p_detach()
+        f_nccl = eng.fit_flat(mu8, cov8, w8, cov_type="full", max_iter=8)
+        hdist.reattach_p2p(eng)              # (its self-test replaces the engine's cloud)
+        eng.set_points(shard, total=len(X))
+    else:
+        f_nccl = f_p2p
+    L = 3
+    init = X[H.reference_init_indices(L)]
+    tkw = dict(ls=20.0, ld=1e-4, sig2=4e-4, want_current=False)
+    t_est = eng.fit_tree(init, L, ll_mode="estep", **tkw)
+    th = np.deg2rad(6.0)
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    T = (X @ R.T + np.array([0.002, -0.001, 0.003])).astype(np.float32)
+    eng.reg_set_target(hdist.shuffled_shard(T, rank, world, seed=6))
+    rot, t, q, it, _ = eng.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+    t_lvl = eng.fit_tree(init, L, ll_mode="level", **tkw)
+    Jr = 100
+    mur, covr, wr = init_model(X, seed=4, j=Jr)
+    eng.fit_flat(mur, covr, wr, cov_type="full", max_iter=10, want_outputs=False)
+    frot, ft, fq, fit_, _ = eng.register_flat(solver="procrustes_svd", maxiter=15, tol=1e-9)
+    out = None
+    if rank == 0:
+        ref = hgmm_b200.Engine(local)
+        ref.set_points(X)
+        s8 = ref.fit_flat(mu8, cov8, w8, cov_type="full", max_iter=8)
+        s_est = ref.fit_tree(init, L, ll_mode="estep", **tkw)
+        ref.reg_set_target(T)
+        rot1, t1, q1, it1, _ = ref.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+        s_lvl = ref.fit_tree(init, L, ll_mode="level", **tkw)
+        ref.fit_flat(mur, covr, wr, cov_type="full", max_iter=10, want_outputs=False)
+        frot1, ft1, fq1, fit1, _ = ref.register_flat(solver="procrustes_svd", maxiter=15, tol=1e-9)
+        ref.close()
+        errs = {
+            "flat_J800_peer_memory" if p2p_on else "flat_J800_nccl": max(rel_fro(f_p2p[k], s8[k]) for k in ("means", "covs", "weights", "ll")),
+            "flat_J800_nccl": max(rel_fro(f_nccl[k], s8[k]) for k in ("means", "covs", "weights", "ll")),
+            "tree_L3_ll_estep": max(rel_fro(t_est[k], s_est[k]) for k in ("pi", "mu", "cov")),
+            "tree_L3_ll_level": max(rel_fro(t_lvl[k], s_lvl[k]) for k in ("pi", "mu", "cov")),
+            "tree_registration": max(rel_fro(rot, rot1), float(np.abs(t - t1).max())),
+            "flat_registration": max(rel_fro(frot, frot1), float(np.abs(ft - ft1).max())),
+        }
+        iters_equal = bool(t_est["iters"].tolist() == s_est["iters"].tolist() and t_lvl["iters"].tolist() == s_lvl["iters"].tolist()
+                           and it == it1 and fit_ == fit1)
+        out = {"max_rel_fro": errs, "iters_equal": iters_equal, "tolerance": PARITY_TOL, "peer_memory": bool(p2p_on),
+               "iters": {"tree_estep": [t_est["iters"].tolist(), s_est["iters"].tolist()], "tree_level": [t_lvl["iters"].tolist(), s_lvl["iters"].tolist()],
+                         "tree_registration": [int(it), int(it1)], "flat_registration": [int(fit_), int(fit1)]},
+               "cloud": "every 2nd bun000 vertex (20128 pts), shards of a seeded shuffle", "ok": bool(max(errs.values()) < PARITY_TOL and iters_equal)}
+    return out if rank == 0 else {"ok": True}
 
 
 if __name__ == "__main__":

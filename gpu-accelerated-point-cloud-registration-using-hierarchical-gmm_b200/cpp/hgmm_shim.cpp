@@ -110,6 +110,43 @@ void GMMRegistration::initSimulation(int N1, glm::vec3* src_pc, int N2, glm::vec
 
 void GMMRegistration::pointCloudRegisterGPU(float /*dt*/) {
     hgmm_ctx* c = static_cast<hgmm_ctx*>(engine);
+    // Default: what the class's fields describe (numComponents means dev_srcMu / weights dev_srcPsi, gmm_reg.h:8-20) -- a FLAT
+    // K-component full-covariance mixture of the source (10 EM iterations, the fit driver's count, gmm_kernels.cu:588) and the
+    // weighted-Procrustes registration of the target against it (BASELINE configs[3]).  HGMM_SHIM_REG=tree selects the
+    // hierarchical mixture + linearised twist solve of src/python/hgmm instead.
+    const char* mode = getenv("HGMM_SHIM_REG");
+    if (!(mode && strcmp(mode, "tree") == 0)) {
+        if (!treeBuilt) {
+            const int K = numComponents;
+            vector<float> mu0((size_t)K * 3), cov0((size_t)K * 9, 0.f), w0((size_t)K, 1.0f / K);
+            float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+            for (const glm::vec3& p : srcHost) {
+                lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+                lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+                lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+            }
+            const float ext = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
+            const float s0 = (ext / 16) * (ext / 16);          // data-scaled start (the fitter's Sigma = I is for unit-scale data)
+            unsigned s = 72u;
+            for (int j = 0; j < K; ++j) {                      // seeded draw of K source points (gmm_kernels.cu:374-379 uses rand())
+                s = s * 1664525u + 1013904223u;
+                const glm::vec3& p = srcHost[s % (unsigned)numSrcPc];
+                mu0[3 * j] = p.x; mu0[3 * j + 1] = p.y; mu0[3 * j + 2] = p.z;
+                cov0[9 * j] = cov0[9 * j + 4] = cov0[9 * j + 8] = s0;
+            }
+            hgmm_flat_config fc;
+            memset(&fc, 0, sizeof fc);
+            fc.n_components = K; fc.cov_type = HGMM_COV_FULL; fc.flavor = HGMM_FLAVOR_CPP; fc.max_iter = 10;
+            CHECK(c, hgmm_fit_flat(c, &fc, mu0.data(), cov0.data(), w0.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+            treeBuilt = true;
+        }
+        hgmm_reg_config rc;
+        rc.solver = HGMM_SOLVER_PROCRUSTES; rc.maxiter = 20; rc.tol = 1e-4f; rc.lambda_c = 0.f;
+        double q = 0;
+        int32_t it = 0;
+        CHECK(c, hgmm_register_flat(c, &rc, rot, trans, &q, &it, nullptr));
+        return;
+    }
     // depth from the component budget K: the deepest tree whose leaf count does not exceed K (K=100 -> 64 leaves, L=2)
     int L = 1;
     while (L < 5 && 8 * (1 << (3 * L)) <= numComponents) ++L;

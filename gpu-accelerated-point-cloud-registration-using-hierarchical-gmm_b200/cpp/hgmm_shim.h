@@ -69,8 +69,9 @@ public:
     GMMRegistration(int K);
 
     void initSimulation(int N1, glm::vec3* src_pc, int N2, glm::vec3* target_pc);
-    // one registration solve (the reference body is empty, gmm_reg.cu:54-56): builds the hierarchical mixture of the
-    // source on first use, registers the target against it and updates dev_srcTransPc / the accumulated transform
+    // one registration solve (the reference body is empty, gmm_reg.cu:54-56): fits the K-component mixture of the source on
+    // first use (flat full-covariance; HGMM_SHIM_REG=tree: the hierarchical one), registers the target against it and
+    // updates the accumulated transform
     void pointCloudRegisterGPU(float dt);
     void copyBoidsToVBO(float* vbodptr_positions, float* vbodptr_velocities);
     void endSimulation();

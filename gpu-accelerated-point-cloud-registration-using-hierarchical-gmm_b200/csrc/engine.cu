@@ -15,6 +15,7 @@
 
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -109,6 +110,7 @@ struct hgmm_ctx {
     // points (this rank's shard), SoA
     int n = 0;
     int64_t n_total = 0;
+    int64_t declared_total = 0;     // hgmm_declare_total_points: > 0 replaces the all-reduce of hgmm_set_points
     DevBuf bx, by, bz, stage;
 
     // shared small state
@@ -132,12 +134,18 @@ struct hgmm_ctx {
     bool have_tree = false;
     DevBuf t_pi, t_mu, t_cov, t_cplx, t_packed, t_init;
     DevBuf wx[2], wy[2], wz[2], wperm[2], wpnode[2], wslot[2], wcpar[2], wcstart[2], wclen[2];
-    DevBuf gbar;                // persistent level kernel: grid barrier words
+    DevBuf gbar;                // persistent level kernel: grid barrier arrival counter
+    DevBuf tprof;               // HGMM_TREE_PROF=1: per-CTA phase clocks of the persistent level kernel
+    DevBuf twin;                // persistent level kernel, single rank: the local "exchange" region (tree_win_layout)
+    int twin_levels = 0;
+    uint32_t tepoch = 16;       // tag base of the next tree level (monotonic over the context's life; identical on every rank)
+    int* h_lvl = nullptr;       // pinned, 8 levels x 8 ints: the control words of every level of the last tree build
     DevBuf p_group, p_tilecnt, p_tileoff, p_segbase, p_seg0, p_seg1, p_chunkcnt, p_chunkoff, nchunks, current;
 
     // registration
     int nt_pts = 0;
     DevBuf tx, ty, tz, racc, Rt;
+    DevBuf rx, ry, rz;          // flat registration: the target under the current transform
     bool have_target = false;
     bool have_racc = false;
 
@@ -153,6 +161,8 @@ struct hgmm_ctx {
     void* xpeer[kXchgMaxRanks] = {};      // every rank's window as mapped here (own entry = xwin)
     bool p2p_ready = false;
     uint32_t xepoch = 0;
+    int xwin_tree_levels = 0;             // deepest tree the window's tree region was sized for (0: none)
+    double xchg_timeout_s = 30.0;         // deadline of every in-kernel wait on a peer (HGMM_XCHG_TIMEOUT_S)
 };
 
 #define CK(call)                                                                                  \
@@ -232,6 +242,7 @@ int hgmm_create(hgmm_ctx** out, int device, void* stream) {
     if (cudaMallocHost((void**)&ctx->h_ctrl, 8 * sizeof(int)) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_dbl, 64 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_params, (size_t)kMaxFlatJ * 13 * sizeof(float)) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_lvl, 64 * sizeof(int)) != cudaSuccess ||
         cudaHostAlloc((void**)&ctx->h_prog, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&ctx->d_prog, ctx->h_prog, 0) != cudaSuccess ||
         ctx->ctrl.ensure(8 * sizeof(int)) != cudaSuccess ||
@@ -239,6 +250,10 @@ int hgmm_create(hgmm_ctx** out, int device, void* stream) {
         ctx->Rt.ensure(12 * sizeof(double)) != cudaSuccess) {
         hgmm_destroy(ctx);
         return HGMM_ERR_CUDA;
+    }
+    if (const char* e = getenv("HGMM_XCHG_TIMEOUT_S")) {
+        const double v = atof(e);
+        if (v > 0.0) ctx->xchg_timeout_s = v;
     }
     *out = ctx;
     return HGMM_OK;
@@ -254,7 +269,7 @@ int hgmm_destroy(hgmm_ctx* ctx) {
                      &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->done_at, &ctx->partial, &ctx->rowaux, &ctx->cref, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
                      &ctx->t_cplx, &ctx->t_packed, &ctx->t_init, &ctx->p_group, &ctx->p_tilecnt, &ctx->p_tileoff, &ctx->p_segbase,
                      &ctx->p_seg0, &ctx->p_seg1, &ctx->p_chunkcnt, &ctx->p_chunkoff, &ctx->nchunks, &ctx->current, &ctx->tx, &ctx->ty,
-                     &ctx->tz, &ctx->racc, &ctx->Rt, &ctx->l2buf, &ctx->gbar};
+                     &ctx->tz, &ctx->racc, &ctx->Rt, &ctx->l2buf, &ctx->gbar, &ctx->twin, &ctx->rx, &ctx->ry, &ctx->rz, &ctx->tprof};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < 2; ++i) {
         DevBuf* w[] = {&ctx->wx[i], &ctx->wy[i], &ctx->wz[i], &ctx->wperm[i], &ctx->wpnode[i], &ctx->wslot[i], &ctx->wcpar[i],
@@ -265,6 +280,7 @@ int hgmm_destroy(hgmm_ctx* ctx) {
     if (ctx->h_dbl) cudaFreeHost(ctx->h_dbl);
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
     if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
+    if (ctx->h_lvl) cudaFreeHost(ctx->h_lvl);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
@@ -300,6 +316,11 @@ static int upload_cloud(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind
     else launch_aos_to_soa(src, n, X.as<float>(), Y.as<float>(), Z.as<float>(), ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
+    // A caller's DEVICE buffer is read by the conversion kernel on the context's stream: wait for it, so the buffer may be freed
+    // or overwritten as soon as this call returns.  HOST input: pageable memory has been staged by the runtime when
+    // cudaMemcpyAsync returns; PINNED memory is read by the copy engine later and must stay untouched until the next call that
+    // synchronises (any fit / predict / register) -- documented in include/hgmm.h, the Python wrapper holds a reference.
+    if (mem_kind == HGMM_MEM_DEVICE) CK(cudaStreamSynchronize(ctx->stream));
     return HGMM_OK;
 }
 
@@ -309,7 +330,9 @@ int hgmm_set_points(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind) {
     if (r != HGMM_OK) return r;
     ctx->n = (int)n;
     ctx->n_total = n;
-    if (ctx->comm && ctx->nranks > 1) {
+    if (ctx->comm && ctx->nranks > 1 && ctx->declared_total > 0) {
+        ctx->n_total = ctx->declared_total;      // the caller sharded the cloud and knows the total: no collective, no sync
+    } else if (ctx->comm && ctx->nranks > 1) {
         // total point count over ranks (the tree's pi = M0 / N_total, hgmm_gpu.py:257)
         double* d = ctx->qstate.as<double>();
         ctx->h_dbl[0] = (double)n;
@@ -320,6 +343,14 @@ int hgmm_set_points(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind) {
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->n_total = (int64_t)(ctx->h_dbl[0] + 0.5);
     }
+    return HGMM_OK;
+}
+
+int hgmm_declare_total_points(hgmm_ctx* ctx, int64_t n_total) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (n_total < 0) FAIL(HGMM_ERR_INVALID, "negative total");
+    ctx->declared_total = n_total;
+    if (n_total > 0 && ctx->nranks > 1) ctx->n_total = n_total;
     return HGMM_OK;
 }
 
@@ -415,6 +446,7 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
                 XchgView xv;
                 for (int r = 0; r < kXchgMaxRanks; ++r) xv.data[r] = reinterpret_cast<uint4*>(ctx->xpeer[r]);
                 xv.rank = ctx->rank; xv.nranks = ctx->nranks; xv.epoch = ++ctx->xepoch;
+                xv.timeout_ns = (unsigned long long)(ctx->xchg_timeout_s * 1e9);
                 CK(launch_flat_reduce_exchange_finalize(m, ctx->partial.as<float>(), ctx->rowaux.as<double>(), grid * G,
                                                         ctx->ctrl.as<int>(), done_at, it, ctx->hist.as<double>(),
                                                         (double)ctx->n_total, xv, s));
@@ -558,7 +590,7 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
     CK(ctx->p_chunkcnt.ensure((size_t)max_newseg * sizeof(int)));
     CK(ctx->p_chunkoff.ensure((size_t)(max_newseg + 1) * sizeof(int)));
     const size_t acc_n = kAccHdr + (size_t)level_count_h(L - 1) * kMom;
-    CK(ctx->acc.ensure(acc_n * sizeof(double)));
+    CK(ctx->acc.ensure(2 * acc_n * sizeof(double)));          // two parities for the persistent level kernel
     CK(ctx->t_init.ensure((size_t)t.nt * 3 * sizeof(float)));
 
     TreeWork w[2];
@@ -594,7 +626,88 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
     const bool fast_ll = cfg->ll_mode == HGMM_LL_ESTEP;
     CK(ctx->done_at.ensure((size_t)(max_iters + batch + 4) * sizeof(int)));
     int* done_at = ctx->done_at.as<int>();
-    for (int l = 0; l < L; ++l) {
+    // Default (fast log-likelihood mode): ONE persistent cooperative kernel per level (tree_level.cuh) -- on several ranks with
+    // the reduce-scatter / all-gather of the level's statistics fused in over peer memory, no NCCL call, no host round trip.
+    // The multi-kernel path below stays for HGMM_LL_LEVEL (the reference's whole-level scan), the scalar A/B kernel, ranks
+    // without peer-memory windows, and HGMM_TREE_LEGACY=1.
+    static const bool legacy_env = getenv("HGMM_TREE_LEGACY") && getenv("HGMM_TREE_LEGACY")[0] == '1';
+    const bool persist = fast_ll && cfg->reserved == 0 && !legacy_env &&
+                         (ctx->nranks <= 1 || (ctx->p2p_ready && L <= ctx->xwin_tree_levels));
+    TreeXchgHost xh{};
+    if (persist) {
+        xh.rank = ctx->rank; xh.nranks = ctx->nranks;
+        xh.timeout_ns = (unsigned long long)(ctx->xchg_timeout_s * 1e9);
+        if (ctx->nranks <= 1) {
+            xh.rank = 0; xh.nranks = 1;
+            const TreeWinLayout wl = tree_win_layout(L);
+            if (ctx->twin_levels < L) {
+                CK(ctx->twin.ensure(wl.bytes));
+                CK(cudaMemsetAsync(ctx->twin.p, 0, wl.bytes, s));
+                ctx->twin_levels = L;
+            }
+            const TreeWinLayout cur_l = tree_win_layout(ctx->twin_levels);
+            char* base = ctx->twin.as<char>();
+            xh.pk[0] = base + cur_l.pk_off; xh.fin[0] = base + cur_l.fin_off; xh.mom[0] = base + cur_l.mom_off; xh.ll[0] = base + cur_l.ll_off;
+            xh.mom_cap = cur_l.mom_cap;
+        } else {
+            const TreeWinLayout wl = tree_win_layout(ctx->xwin_tree_levels);
+            for (int r = 0; r < ctx->nranks; ++r) {
+                char* base = static_cast<char*>(ctx->xpeer[r]) + kXchgBytes;
+                xh.pk[r] = base + wl.pk_off; xh.fin[r] = base + wl.fin_off; xh.mom[r] = base + wl.mom_off; xh.ll[r] = base + wl.ll_off;
+            }
+            xh.mom_cap = wl.mom_cap;
+        }
+        CK(ctx->gbar.ensure(4 * sizeof(unsigned)));
+        static const bool prof_env = getenv("HGMM_TREE_PROF") && getenv("HGMM_TREE_PROF")[0] == '1';
+        if (prof_env) {            // per-phase SM-clock totals of every CTA, dumped to stderr after the build (diagnostic switch)
+            CK(ctx->tprof.ensure((size_t)ctx->num_sms * 8 * sizeof(long long)));
+            CK(cudaMemsetAsync(ctx->tprof.p, 0, (size_t)ctx->num_sms * 8 * sizeof(long long), s));
+        }
+    }
+    long long* tprof = (persist && ctx->tprof.p) ? ctx->tprof.as<long long>() : nullptr;
+    for (int l = 0; l < L && persist; ++l) {
+        const int64_t cnt = level_count_h(l);
+        const size_t stride = kAccHdr + (size_t)cnt * kMom;
+        CK(cudaMemsetAsync(ctrl, 0, 8 * sizeof(int), s));
+        CK(cudaMemsetAsync(qstate, 0, 4 * sizeof(double), s));
+        CK(cudaMemsetAsync(ctx->gbar.p, 0, 4 * sizeof(unsigned), s));
+        CK(cudaMemsetAsync(acc, 0, 2 * stride * sizeof(double), s));
+        xh.base = ctx->tepoch;
+        ctx->tepoch += (uint32_t)max_iters + 2u;
+        cudaError_t e = launch_tree_level(w[cur], t, l, n, acc, stride, nchunks_dev, (double)ctx->n_total, cfg->ld, cfg->ls, max_iters,
+                                          ctrl, qstate, ctx->gbar.as<unsigned>(), chunk, xh, ctx->num_sms, tprof, s);
+        if (e != cudaSuccess) { ctx->err = std::string("tree level kernel launch: ") + cudaGetErrorString(e); return HGMM_ERR_CUDA; }
+        ctx->launches += 1;
+        // no host synchronisation between levels: the control words of every level are fetched asynchronously, read at the end
+        CK(cudaMemcpyAsync(ctx->h_lvl + 8 * l, ctrl, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_dbl + 32 + 2 * l, qstate, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (l < L - 1) {
+            CK(launch_partition(w[cur], w[1 - cur], n, (int)n_parents, ps, chunk, nchunks_dev, s));
+            ctx->launches += 7;
+            cur = 1 - cur;
+            n_parents *= 8;
+        }
+    }
+    if (persist) {
+        CK(cudaStreamSynchronize(s));
+        if (tprof) {
+            std::vector<long long> h((size_t)ctx->num_sms * 8);
+            CK(cudaMemcpy(h.data(), tprof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            double tot[6] = {0, 0, 0, 0, 0, 0};
+            for (int b = 0; b < ctx->num_sms; ++b)
+                for (int k = 0; k < 6; ++k) tot[k] += (double)h[(size_t)b * 8 + k] / ctx->num_sms;
+            fprintf(stderr, "HGMM_TREE_PROF mean SM cycles per CTA over the build: E %.0f | fold+flush %.0f | barrier %.0f | exchange+M %.0f | verdict %.0f\n",
+                    tot[0], tot[1], tot[2], tot[3], tot[4]);
+        }
+        for (int l = 0; l < L; ++l) {
+            if (ctx->h_lvl[8 * l + 7])
+                FAIL(HGMM_ERR_NCCL, "tree level kernel: a wait on a peer rank timed out (rank missing, or the ranks' call sequences differ)");
+            if (!ctx->h_lvl[8 * l]) FAIL(HGMM_ERR_CUDA, "tree level kernel ended without a verdict");
+            if (out_iters) out_iters[l] = ctx->h_lvl[8 * l + 1];
+            if (out_q) out_q[l] = ctx->h_dbl[32 + 2 * l + 1];
+        }
+    }
+    for (int l = 0; l < L && !persist; ++l) {
         CK(cudaMemsetAsync(ctrl, 0, 8 * sizeof(int), s));
         CK(cudaMemsetAsync(qstate, 0, 4 * sizeof(double), s));
         CK(cudaMemsetAsync(done_at, 0, (size_t)(max_iters + batch + 4) * sizeof(int), s));
@@ -624,18 +737,7 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
             ++it;
             return HGMM_OK;
         };
-        static const bool persist = getenv("HGMM_TREE_PERSIST") && getenv("HGMM_TREE_PERSIST")[0] == '1';     // draft switch
-        if (persist && ctx->nranks <= 1 && fast_ll && cfg->reserved != 1) {
-            // DRAFT (tree_level_kernel): the whole EM loop of the level in one cooperative launch
-            CK(ctx->gbar.ensure(2 * sizeof(unsigned)));
-            CK(cudaMemsetAsync(ctx->gbar.p, 0, 2 * sizeof(unsigned), s));
-            CK(launch_tree_level(w[cur], t, l, acc, chunks_bound, nchunks_dev, (double)ctx->n_total, cfg->ld, cfg->ls, max_iters, ctrl,
-                                 qstate, ctx->gbar.as<unsigned>(), ctx->num_sms, s));
-            ctx->launches += 1;
-            CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            done = true;
-        } else if (ctx->nranks <= 1) {
+        if (ctx->nranks <= 1) {
             // single rank: no stream synchronise inside the level.  The kernel that evaluates the stopping rule also writes
             // (converged, iterations retired) to host-mapped memory; the host keeps at most `ahead` iterations in flight and
             // stops enqueuing when it sees the flag (iterations already enqueued are no-ops through done_at).
@@ -643,11 +745,21 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
             prog[0] = 0;
             prog[1] = 0;
             const int ahead = 6;
-            const auto t_start = std::chrono::steady_clock::now();
+            // watchdog: "no new iteration retired for 120 s" (re-armed on every advance of prog[0]) or a dead stream --
+            // never a bound on the level's total run time; the wait yields the core instead of spinning flat out
+            auto t_progress = std::chrono::steady_clock::now();
+            int seen = 0;
             while (true) {
                 bool stalled = false;
+                unsigned polls = 0;
                 while (it - prog[0] >= ahead && !prog[1]) {
-                    if (std::chrono::steady_clock::now() - t_start > std::chrono::seconds(120)) { stalled = true; break; }
+                    if (prog[0] != seen) { seen = prog[0]; t_progress = std::chrono::steady_clock::now(); }
+                    if ((++polls & 1023u) == 0u) {
+                        std::this_thread::yield();
+                        const cudaError_t q = cudaStreamQuery(s);
+                        if (q != cudaSuccess && q != cudaErrorNotReady) { stalled = true; break; }
+                        if (std::chrono::steady_clock::now() - t_progress > std::chrono::seconds(120)) { stalled = true; break; }
+                    }
                 }
                 if (stalled || prog[1] || it >= max_iters + batch) break;
                 r = enqueue_iteration(ctx->d_prog);
@@ -786,20 +898,31 @@ int hgmm_reg_mstep(hgmm_ctx* ctx, int32_t solver, double* rot, double* t, double
     int r = upload_Rt(ctx, rot, t);
     if (r != HGMM_OK) return r;
     cudaStream_t s = ctx->stream;
-    CK(ctx->hist.ensure(8 * sizeof(double)));
+    CK(ctx->hist.ensure(64 * sizeof(double)));
     CK(cudaMemsetAsync(ctx->ctrl.p, 0, 8 * sizeof(int), s));
     CK(cudaMemsetAsync(ctx->qstate.p, 0, 4 * sizeof(double), s));
     CK(launch_reg_solve(ctx->tm, ctx->racc.as<double>(), 0, solver, ctx->Rt.as<double>(), ctx->hist.as<double>(),
                         ctx->qstate.as<double>(), ctx->ctrl.as<int>(), 0.f, s));
     ctx->launches += 1;
     CK(cudaMemcpyAsync(ctx->h_dbl, ctx->Rt.p, 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(ctx->h_dbl + 16, ctx->qstate.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_dbl + 16, ctx->qstate.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     for (int k = 0; k < 9; ++k) rot[k] = ctx->h_dbl[k];
     for (int k = 0; k < 3; ++k) t[k] = ctx->h_dbl[9 + k];
     if (out_q) *out_q = ctx->h_dbl[17];
-    if (ctx->h_ctrl[2]) FAIL(HGMM_ERR_NUMERIC, "registration solve: singular / non-positive-definite system");
+    if (ctx->h_ctrl[2]) {
+        std::string msg = "registration solve: singular / non-positive-definite system";
+        if (solver == HGMM_SOLVER_TWIST_LSTSQ) {          // the 28 sums of the failed normal equations, for the bug report
+            double hv[28];
+            if (cudaMemcpy(hv, ctx->hist.as<double>() + 8, sizeof hv, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                msg += " v =";
+                char b[40];
+                for (double x : hv) { snprintf(b, sizeof b, " %.17g", x); msg += b; }
+            }
+        }
+        FAIL(HGMM_ERR_NUMERIC, msg);
+    }
     return HGMM_OK;
 }
 
@@ -856,6 +979,86 @@ int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, d
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_ms[0] = ms; ctx->last_ms[1] = ms; ctx->last_ms[2] = 0;
     ctx->have_racc = false;       // the loop's solve kernel consumed (zeroed) the moments
+    if (ctx->h_ctrl[2]) FAIL(HGMM_ERR_NUMERIC, "registration solve: singular / non-positive-definite system");
+    return HGMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// flat-mixture registration: model = the context's flat mixture (hgmm_fit_flat), target = hgmm_reg_set_target
+// (GMMRegistration::pointCloudRegisterGPU, src/c++/gmm_registration/gmm_reg.cu:54-56 -- an empty stub in the reference)
+// ------------------------------------------------------------------------------------------
+int hgmm_register_flat(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, double* t, double* out_q, int32_t* out_iters,
+                       double* out_q_hist) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!cfg || !rot || !t) FAIL(HGMM_ERR_INVALID, "null config / transform");
+    if (!ctx->have_flat) FAIL(HGMM_ERR_STATE, "no flat model: call hgmm_fit_flat first");
+    if (!ctx->have_target) FAIL(HGMM_ERR_STATE, "no target: call hgmm_reg_set_target first");
+    if (cfg->solver != HGMM_SOLVER_TWIST_LSTSQ && cfg->solver != HGMM_SOLVER_PROCRUSTES) FAIL(HGMM_ERR_INVALID, "unknown solver");
+    if (cfg->maxiter < 1 || cfg->maxiter > 100000) FAIL(HGMM_ERR_INVALID, "bad maxiter");
+    const FlatModel& m = ctx->fm;
+    if (cfg->solver == HGMM_SOLVER_TWIST_LSTSQ && m.cov_type != HGMM_COV_FULL)
+        FAIL(HGMM_ERR_INVALID, "the twist solver needs full covariances; use HGMM_SOLVER_PROCRUSTES with diag / spherical mixtures");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->nt_pts;
+    if (n <= 0) FAIL(HGMM_ERR_STATE, "empty target");
+    const size_t fb = (size_t)n * sizeof(float);
+    CK(ctx->rx.ensure(fb)); CK(ctx->ry.ensure(fb)); CK(ctx->rz.ensure(fb));
+    const size_t acc_n = kAccHdr + (size_t)m.Jp * kMom;
+    CK(ctx->acc.ensure(acc_n * sizeof(double)));
+    CK(ctx->hist.ensure((size_t)(cfg->maxiter + 1) * sizeof(double)));
+    // sweep plan for the target's size (the kernels of the fit; the PDL-chained flat_em7 stages its points before the grid
+    // dependency resolves, which is only valid for a cloud that does not change between launches -- here it does)
+    const bool v3 = m.Jp >= 64;
+    int JT = 1, W = 8, Sdiv = 1, G = 1, grid = 1, big = 0;
+    if (v3) flat3_plan(n, m.Jp, ctx->num_sms, ((m.Jp / 32 + 1) / 2 >= 9) ? 6 : 0, &W, &Sdiv, &G, &grid, &big);
+    else flat2_plan(n, m.Jp, ctx->num_sms, 0, &JT, &W, &Sdiv, &G, &grid, &big);
+    CK(ctx->partial.ensure((size_t)grid * G * kMom * m.Jp * sizeof(float)));
+    CK(ctx->rowaux.ensure((size_t)grid * G * 2 * sizeof(double)));
+    int r = upload_Rt(ctx, rot, t);
+    if (r != HGMM_OK) return r;
+    cudaStream_t s = ctx->stream;
+    int* ctrl = ctx->ctrl.as<int>();
+    CK(cudaMemsetAsync(ctrl, 0, 8 * sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->qstate.p, 0, 4 * sizeof(double), s));
+    CK(cudaMemsetAsync(ctx->acc.p, 0, acc_n * sizeof(double), s));
+    CK(cudaEventRecord(ctx->ev0, s));
+    const int batch = 4;
+    int issued = 0;
+    bool done = false;
+    while (!done && issued < cfg->maxiter) {
+        for (int b = 0; b < batch && issued < cfg->maxiter; ++b, ++issued) {
+            launch_transform_soa(ctx->tx.as<float>(), ctx->ty.as<float>(), ctx->tz.as<float>(), n, ctx->Rt.as<double>(),
+                                 ctx->rx.as<float>(), ctx->ry.as<float>(), ctx->rz.as<float>(), ctrl, s);
+            if (v3)
+                CK(launch_em_flat3(ctx->rx.as<float>(), ctx->ry.as<float>(), ctx->rz.as<float>(), n, m, m.cref_blocks, W, Sdiv, G, grid, big,
+                                   ctx->partial.as<float>(), ctx->rowaux.as<double>(), ctrl, s));
+            else
+                CK(launch_em_flat2(ctx->rx.as<float>(), ctx->ry.as<float>(), ctx->rz.as<float>(), n, m, m.cref_blocks, JT, W, Sdiv, G, grid,
+                                   big, ctx->partial.as<float>(), ctx->rowaux.as<double>(), ctrl, s));
+            CK(launch_flat_reduce(ctx->partial.as<float>(), ctx->rowaux.as<double>(), grid * G, m, ctx->acc.as<double>(), ctrl, s));
+            r = allreduce(ctx, ctx->acc.as<double>(), kAccHdr + (size_t)m.J * kMom);
+            if (r != HGMM_OK) return r;
+            CK(launch_reg_flat_solve(m, ctx->acc.as<double>(), cfg->solver, ctx->Rt.as<double>(), ctx->hist.as<double>(),
+                                     ctx->qstate.as<double>(), ctrl, cfg->tol, s));
+            ctx->launches += 4;
+        }
+        CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        done = ctx->h_ctrl[0] != 0;
+    }
+    CK(cudaEventRecord(ctx->ev1, s));
+    const int iters = ctx->h_ctrl[1];
+    CK(cudaMemcpyAsync(ctx->h_dbl, ctx->Rt.p, 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_dbl + 16, ctx->qstate.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out_q_hist && iters > 0) CK(cudaMemcpyAsync(out_q_hist, ctx->hist.p, (size_t)iters * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < 9; ++k) rot[k] = ctx->h_dbl[k];
+    for (int k = 0; k < 3; ++k) t[k] = ctx->h_dbl[9 + k];
+    if (out_q) *out_q = ctx->h_dbl[17];
+    if (out_iters) *out_iters = iters;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms[0] = ms; ctx->last_ms[1] = ms; ctx->last_ms[2] = 0;
     if (ctx->h_ctrl[2]) FAIL(HGMM_ERR_NUMERIC, "registration solve: singular / non-positive-definite system");
     return HGMM_OK;
 }
@@ -993,9 +1196,18 @@ int hgmm_p2p_export(hgmm_ctx* ctx, void* out_handle64) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->xwin) {
-        CK(cudaMalloc(&ctx->xwin, kXchgBytes));
-        CK(cudaMemset(ctx->xwin, 0, kXchgBytes));
+        // flat region (xchg.cuh) followed by the tree region (tree_level.cuh), sized for trees up to HGMM_P2P_TREE_LEVELS
+        // (default 5: 16 MB; 6 needs 131 MB).  Always a freshly zeroed allocation: tags / epochs only grow over the context's
+        // life (never reset on re-attach), so no stale cell can ever validate.
+        int lv = 5;
+        if (const char* e = getenv("HGMM_P2P_TREE_LEVELS")) lv = atoi(e);
+        if (lv < 0) lv = 0;
+        if (lv > 6) lv = 6;
+        const size_t bytes = kXchgBytes + (lv > 0 ? tree_win_layout(lv).bytes : 0);
+        CK(cudaMalloc(&ctx->xwin, bytes));
+        CK(cudaMemset(ctx->xwin, 0, bytes));
         CK(cudaDeviceSynchronize());
+        ctx->xwin_tree_levels = lv;
     }
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, ctx->xwin));
@@ -1026,8 +1238,7 @@ int hgmm_p2p_attach(hgmm_ctx* ctx, const void* handles, int32_t n_handles) {
         }
         ctx->xpeer[r] = p;
     }
-    ctx->xepoch = 0;
-    ctx->p2p_ready = true;
+    ctx->p2p_ready = true;               // xepoch / tepoch keep counting: see hgmm_p2p_export
     return HGMM_OK;
 }
 

@@ -66,10 +66,19 @@ inline void put(float* out, int64_t cap, int64_t i, const std::vector<std::strin
 
 extern "C" {
 
+static int read_ply_impl(const char* path, int32_t mode, float* out_xyz, int64_t capacity, int64_t* out_n);
 int hgmm_io_read_ply(const char* path, int32_t mode, float* out_xyz, int64_t capacity, int64_t* out_n) {
     if (!path || !out_n || capacity < 0 || (capacity > 0 && !out_xyz)) return HGMM_ERR_INVALID;
     if (mode != HGMM_PLY_HEADER && mode != HGMM_PLY_VIEWER_FIT && mode != HGMM_PLY_VIEWER_REG) return HGMM_ERR_INVALID;
     *out_n = 0;
+    try {
+        return read_ply_impl(path, mode, out_xyz, capacity, out_n);
+    } catch (...) {
+        *out_n = 0;
+        return HGMM_ERR_IO;
+    }
+}
+static int read_ply_impl(const char* path, int32_t mode, float* out_xyz, int64_t capacity, int64_t* out_n) {
     std::ifstream in(path, std::ios::binary);
     if (!in.is_open()) return HGMM_ERR_IO;
     std::string line;
@@ -140,9 +149,18 @@ int hgmm_io_read_ply(const char* path, int32_t mode, float* out_xyz, int64_t cap
     return HGMM_OK;
 }
 
+static int read_pcd_impl(const char* path, float* out_xyz, int64_t capacity, int64_t* out_n);
 int hgmm_io_read_pcd(const char* path, float* out_xyz, int64_t capacity, int64_t* out_n) {
     if (!path || !out_n || capacity < 0 || (capacity > 0 && !out_xyz)) return HGMM_ERR_INVALID;
     *out_n = 0;
+    try {                                    // no exception (bad_alloc on a hostile header, stream failures) crosses the C ABI
+        return read_pcd_impl(path, out_xyz, capacity, out_n);
+    } catch (...) {
+        *out_n = 0;
+        return HGMM_ERR_IO;
+    }
+}
+static int read_pcd_impl(const char* path, float* out_xyz, int64_t capacity, int64_t* out_n) {
     std::ifstream in(path, std::ios::binary);
     if (!in.is_open()) return HGMM_ERR_IO;
     std::string line;
@@ -167,6 +185,14 @@ int hgmm_io_read_pcd(const char* path, float* out_xyz, int64_t capacity, int64_t
     if (points < 0 && width >= 0) points = width * height;
     if (data.empty() || points < 0 || fields.size() < 3 || fields[0] != "x" || fields[1] != "y" || fields[2] != "z") return HGMM_ERR_IO;
     if (sizes.size() != fields.size() || types.size() != fields.size()) return HGMM_ERR_IO;
+    if (!counts.empty() && counts.size() != fields.size()) return HGMM_ERR_IO;           // COUNT must cover every field
+    size_t row_bytes = 0;
+    for (size_t i = 0; i < fields.size(); ++i) {                                          // untrusted header: every SIZE / COUNT
+        const int c = counts.empty() ? 1 : counts[i];                                     // positive, row size bounded
+        if (sizes[i] <= 0 || sizes[i] > 8 || c <= 0 || c > 4096) return HGMM_ERR_IO;
+        row_bytes += (size_t)sizes[i] * (size_t)c;
+        if (row_bytes > (size_t)1 << 20) return HGMM_ERR_IO;
+    }
     for (int i = 0; i < 3; ++i)
         if (sizes[i] != 4 || types[i] != "F" || (!counts.empty() && counts[i] != 1)) return HGMM_ERR_IO;
     if (data == "ascii") {
@@ -177,8 +203,7 @@ int hgmm_io_read_pcd(const char* path, float* out_xyz, int64_t capacity, int64_t
             put(out_xyz, capacity, i, tok);
         }
     } else if (data == "binary") {
-        size_t stride = 0;
-        for (size_t i = 0; i < fields.size(); ++i) stride += (size_t)sizes[i] * (size_t)(counts.empty() ? 1 : counts[i]);
+        const size_t stride = row_bytes;
         std::vector<char> row(stride);
         for (int64_t i = 0; i < points; ++i) {
             in.read(row.data(), (std::streamsize)stride);

@@ -59,6 +59,7 @@ struct XchgView {
     uint4* data[kXchgMaxRanks];                  // window of rank r (own window: the local pointer)
     int rank, nranks;
     uint32_t epoch;                              // same on every rank; parity selects the half of the window
+    unsigned long long timeout_ns;               // deadline of a wait on a peer
 };
 
 struct TreeModel {
@@ -137,9 +138,40 @@ void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_tota
                        int merge_converge, double* qstate, float ls, int max_iters, int* prog, cudaStream_t s);
 void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, int* prog,
                           cudaStream_t s);
-cudaError_t launch_tree_level(const TreeWork& w, const TreeModel& t, int level, double* acc, int n_chunks_bound,
+// host view of the tree exchange windows (device pointers of every rank's regions; own entries are local allocations)
+struct TreeXchgHost {
+    void* pk[kXchgMaxRanks];
+    void* fin[kXchgMaxRanks];
+    void* mom[kXchgMaxRanks];
+    void* ll[kXchgMaxRanks];
+    int rank, nranks;
+    uint32_t base;
+    unsigned long long mom_cap;
+    unsigned long long timeout_ns;
+};
+// byte layout of one rank's tree exchange region: parameter cells | final-model cells | moment cells [2 parities] | log-lik cells
+struct TreeWinLayout {
+    size_t pk_off, fin_off, mom_off, ll_off, bytes;
+    unsigned long long mom_cap;                  // 16-byte cells per parity
+};
+inline TreeWinLayout tree_win_layout(int max_level) {
+    size_t cnt = 1;
+    for (int i = 0; i < max_level; ++i) cnt *= 8;                                // nodes of the deepest level
+    TreeWinLayout w;
+    w.pk_off = 0;
+    w.fin_off = w.pk_off + cnt * 10 * 8;
+    w.mom_off = w.fin_off + cnt * 10 * 8;
+    w.mom_cap = (unsigned long long)(cnt + 64 * kXchgMaxRanks) * 10;             // R * owned_cap <= cnt + 32 R (+ slack)
+    w.ll_off = w.mom_off + 2 * (size_t)w.mom_cap * 16;
+    w.bytes = w.ll_off + 2 * (size_t)kXchgMaxRanks * 16;
+    return w;
+}
+void tree_level_plan(int n, int chunk_points, int level, int num_sms, int smem_optin, int* pt_cap, int* chunk_cap, int* stage_cap,
+                     size_t* smem_bytes);
+cudaError_t launch_tree_level(const TreeWork& w, const TreeModel& t, int level, int n, double* acc, size_t acc_stride,
                               const int* n_chunks_dev, double n_total, float ld, float ls, int max_iters, int* ctrl, double* qstate,
-                              unsigned* gbar, int num_sms, cudaStream_t s);
+                              unsigned* gbar, int chunk_points, const TreeXchgHost& xh, int num_sms, long long* prof,
+                              cudaStream_t s);
 void launch_tree_zero_ll(double* acc, const int* done_flag, cudaStream_t s);
 void launch_tree_cplx(const TreeModel& t, cudaStream_t s);
 void launch_tree_current(const TreeWork& w, int n, int level, int64_t* current, cudaStream_t s);
@@ -167,6 +199,10 @@ cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, 
                              float lambda_c, double* racc, int want_m2, const int* ctrl, cudaStream_t s);
 cudaError_t launch_reg_solve(const TreeModel& t, double* racc, int zero_after, int solver, double* Rt, double* q_hist,
                              double* qstate, int* ctrl, float tol, cudaStream_t s);
+void launch_transform_soa(const float* tx, const float* ty, const float* tz, int n, const double* Rt, float* ox, float* oy, float* oz,
+                          const int* ctrl, cudaStream_t s);
+cudaError_t launch_reg_flat_solve(const FlatModel& m, const double* acc, int solver, double* Rt, double* q_hist, double* qstate,
+                                  int* ctrl, float tol, cudaStream_t s);
 void launch_zero_doubles(double* p, size_t n, const int* ctrl, cudaStream_t s);
 void launch_fill_vbo(const float* x, const float* y, const float* z, int64_t n, int64_t offset, float* vbo_pos, float* vbo_col,
                      float scene_scale, float r, float g, float b, cudaStream_t s);

@@ -233,6 +233,7 @@ __device__ void block_reduce(double* v, double* sm /*[nwarps][NV]*/, int tid, in
             double t = 0.0;
             for (int w = 0; w < nw; ++w) t += sm[w * NV + k];
             v[k] = t;
+            sm[k] = t;        // the totals also stay in sm[0, NV): column k has been read, later columns are untouched
         }
     }
 }
@@ -387,6 +388,81 @@ __device__ double det3(const double M[3][3]) {
            M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
 }
 
+// ---- the two solves from their reduced sums (thread 0 of the solve kernels) ----
+// `v` is the block's SHARED-memory copy of the totals (block_reduce leaves it in sm[0, NV)).  Passing the kernel's per-thread
+// array instead was miscompiled by nvcc 12.9 for sm_100a once these bodies became functions shared by two kernels: after
+// inlining, H[] was given the stack slots of the still-live v[] (the dumped system showed H's symmetric fill inside v) and
+// every twist solve failed as "not positive definite".
+// v: H (21 upper-triangular) | g (6) | c.  x = H^-1 g (Cholesky), q = c - g^T x (= lstsq's residual, hgmm_gpu.py:746),
+// (R,t) <- twist_mul(x, R, t); stopping rule |q - q_prev| < tol (hgmm_gpu.py:765)
+__device__ __forceinline__ void twist_finish(const double* v, double* Rt, double* q_hist, double* qstate, int* ctrl, float tol) {
+    double H[36], g[6], g0[6];
+    int k = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) { H[6 * a + b] = v[k]; H[6 * b + a] = v[k]; ++k; }
+    for (int a = 0; a < 6; ++a) g[a] = g0[a] = v[21 + a];
+    double q;
+    if (chol6_solve(H, g)) {
+        q = v[27];
+        for (int a = 0; a < 6; ++a) q -= g0[a] * g[a];          // residual sum of squares = c - g^T x
+        double dR[9];
+        rodrigues(g, dR);
+        compose(dR, g + 3, Rt);
+    } else {
+        q = nan("");
+        ctrl[2] = 1;
+        ctrl[0] = 1;
+        qstate[3] = v[0];                 // diagnostics for the host's error message: the failed system itself
+        for (int i = 0; i < kSys; ++i) q_hist[8 + i] = v[i];
+    }
+    const int it = ctrl[1];
+    q_hist[it] = q;
+    if (qstate[2] != 0.0 && fabs(q - qstate[0]) < (double)tol) ctrl[0] = 1;   // hgmm_gpu.py:765
+    qstate[0] = q;
+    qstate[1] = q;
+    qstate[2] = 1.0;
+    ctrl[1] = it + 1;
+}
+
+// v: W | sum w s (3) | sum w mu (3) | sum w s mu^T (9) | sum w |s|^2 | sum w |mu|^2  -> weighted Procrustes (3x3 SVD)
+__device__ __forceinline__ void procrustes_finish(const double* v, double* Rt, double* q_hist, double* qstate, int* ctrl, float tol) {
+    double q = nan("");
+    if (v[0] > 0.0) {
+        const double W = v[0];
+        const double sb[3] = {v[1] / W, v[2] / W, v[3] / W}, mb[3] = {v[4] / W, v[5] / W, v[6] / W};
+        double Hm[3][3];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) Hm[a][b] = v[7 + 3 * a + b] - W * sb[a] * mb[b];    // sum w (s-sb)(m-mb)^T
+        double U[3][3], sig[3], V[3][3];
+        svd3(Hm, U, sig, V);
+        // dR = V diag(1,1,d) U^T with d = det(V U^T)  (reflection fix the reference lacks, icp_kernel.cu:718-729)
+        const double d = (det3(V) * det3(U) < 0.0) ? -1.0 : 1.0;
+        double dR[9];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) dR[3 * a + b] = V[a][0] * U[b][0] + V[a][1] * U[b][1] + d * V[a][2] * U[b][2];
+        double dt[3];
+        for (int a = 0; a < 3; ++a) dt[a] = mb[a] - (dR[3 * a] * sb[0] + dR[3 * a + 1] * sb[1] + dR[3 * a + 2] * sb[2]);
+        // q = sum w |dR (s - sb) - (m - mb)|^2 = Sss + Smm - 2 tr(dR Hm)
+        double tr = 0.0;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) tr += dR[3 * a + b] * Hm[b][a];
+        const double Sss = v[16] - W * (sb[0] * sb[0] + sb[1] * sb[1] + sb[2] * sb[2]);
+        const double Smm = v[17] - W * (mb[0] * mb[0] + mb[1] * mb[1] + mb[2] * mb[2]);
+        q = Sss + Smm - 2.0 * tr;
+        compose(dR, dt, Rt);
+    } else {
+        ctrl[2] = 1;
+        ctrl[0] = 1;
+    }
+    const int it = ctrl[1];
+    q_hist[it] = q;
+    if (qstate[2] != 0.0 && fabs(q - qstate[0]) < (double)tol) ctrl[0] = 1;
+    qstate[0] = q;
+    qstate[1] = q;
+    qstate[2] = 1.0;
+    ctrl[1] = it + 1;
+}
+
 // ctrl: [0] done, [1] iterations, [2] numeric failure flag.  qstate: [0] previous q, [1] last q, [2] has-previous flag
 __global__ void __launch_bounds__(512) reg_solve_kernel(TreeModel t, double* __restrict__ racc, int zero_after, int solver,
                                                         double* __restrict__ Rt, double* __restrict__ q_hist,
@@ -426,32 +502,7 @@ __global__ void __launch_bounds__(512) reg_solve_kernel(TreeModel t, double* __r
             v[27] += M0 * (rr[0] * Pr[0] + rr[1] * Pr[1] + rr[2] * Pr[2]);
         }
         block_reduce<kSys>(v, sm, tid, nth);
-        if (tid == 0) {
-            double H[36], g[6], g0[6];
-            int k = 0;
-            for (int a = 0; a < 6; ++a)
-                for (int b = a; b < 6; ++b) { H[6 * a + b] = v[k]; H[6 * b + a] = v[k]; ++k; }
-            for (int a = 0; a < 6; ++a) g[a] = g0[a] = v[21 + a];
-            double q;
-            if (chol6_solve(H, g)) {
-                q = v[27];
-                for (int a = 0; a < 6; ++a) q -= g0[a] * g[a];          // residual sum of squares = c - g^T x
-                double dR[9];
-                rodrigues(g, dR);
-                compose(dR, g + 3, Rt);
-            } else {
-                q = nan("");
-                ctrl[2] = 1;
-                ctrl[0] = 1;
-            }
-            const int it = ctrl[1];
-            q_hist[it] = q;
-            if (qstate[2] != 0.0 && fabs(q - qstate[0]) < (double)tol) ctrl[0] = 1;   // hgmm_gpu.py:765
-            qstate[0] = q;
-            qstate[1] = q;
-            qstate[2] = 1.0;
-            ctrl[1] = it + 1;
-        }
+        if (tid == 0) twist_finish(sm, Rt, q_hist, qstate, ctrl, tol);
     } else {
         double v[kPro];
         for (int k = 0; k < kPro; ++k) v[k] = 0.0;
@@ -472,43 +523,89 @@ __global__ void __launch_bounds__(512) reg_solve_kernel(TreeModel t, double* __r
             v[17] += w * (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
         }
         block_reduce<kPro>(v, sm, tid, nth);
-        if (tid == 0) {
-            double q = nan("");
-            if (v[0] > 0.0) {
-                const double W = v[0];
-                const double sb[3] = {v[1] / W, v[2] / W, v[3] / W}, mb[3] = {v[4] / W, v[5] / W, v[6] / W};
-                double Hm[3][3];
-                for (int a = 0; a < 3; ++a)
-                    for (int b = 0; b < 3; ++b) Hm[a][b] = v[7 + 3 * a + b] - W * sb[a] * mb[b];    // sum w (s-sb)(m-mb)^T
-                double U[3][3], sig[3], V[3][3];
-                svd3(Hm, U, sig, V);
-                // dR = V diag(1,1,d) U^T with d = det(V U^T)  (reflection fix the reference lacks, icp_kernel.cu:718-729)
-                const double d = (det3(V) * det3(U) < 0.0) ? -1.0 : 1.0;
-                double dR[9];
-                for (int a = 0; a < 3; ++a)
-                    for (int b = 0; b < 3; ++b) dR[3 * a + b] = V[a][0] * U[b][0] + V[a][1] * U[b][1] + d * V[a][2] * U[b][2];
-                double dt[3];
-                for (int a = 0; a < 3; ++a) dt[a] = mb[a] - (dR[3 * a] * sb[0] + dR[3 * a + 1] * sb[1] + dR[3 * a + 2] * sb[2]);
-                // q = sum w |dR (s - sb) - (m - mb)|^2 = Sss + Smm - 2 tr(dR Hm)
-                double tr = 0.0;
-                for (int a = 0; a < 3; ++a)
-                    for (int b = 0; b < 3; ++b) tr += dR[3 * a + b] * Hm[b][a];
-                const double Sss = v[16] - W * (sb[0] * sb[0] + sb[1] * sb[1] + sb[2] * sb[2]);
-                const double Smm = v[17] - W * (mb[0] * mb[0] + mb[1] * mb[1] + mb[2] * mb[2]);
-                q = Sss + Smm - 2.0 * tr;
-                compose(dR, dt, Rt);
-            } else {
-                ctrl[2] = 1;
-                ctrl[0] = 1;
-            }
-            const int it = ctrl[1];
-            q_hist[it] = q;
-            if (qstate[2] != 0.0 && fabs(q - qstate[0]) < (double)tol) ctrl[0] = 1;
-            qstate[0] = q;
-            qstate[1] = q;
-            qstate[2] = 1.0;
-            ctrl[1] = it + 1;
+        if (tid == 0) procrustes_finish(sm, Rt, q_hist, qstate, ctrl, tol);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Flat-mixture registration (BASELINE configs[3] / the north star's "E-step as point-to-mixture correspondence feeding a
+// weighted-Procrustes solve"; the reference's own entry point for it, GMMRegistration::pointCloudRegisterGPU, is an empty
+// stub -- src/c++/gmm_registration/gmm_reg.cu:54-56).  Per iteration: the target under the current (R,t) -> the SAME fused
+// sweep the flat fit uses (responsibilities over all J components, centred moments) -> fixed-order fp64 reduction -> this
+// kernel.  From the centred moments of component j (S0 = sum gamma, S1 = sum gamma (y - mu_j)): mass w_j = S0, centroid of
+// the mass s_j = mu_j + S1/S0; Procrustes aligns {s_j} to {mu_j} with weights w_j, the twist solver minimises
+// sum_j w_j ||J_j x - (mu_j - s_j)||^2 in the Sigma_j^-1 metric (same normal equations as the tree's, full covariances only).
+// ------------------------------------------------------------------------------------------
+__global__ void transform_soa_kernel(const float* __restrict__ tx, const float* __restrict__ ty, const float* __restrict__ tz, int n,
+                                     const double* __restrict__ Rt, float* __restrict__ ox, float* __restrict__ oy,
+                                     float* __restrict__ oz, const int* __restrict__ ctrl) {
+    if (ctrl[0]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = tx[i], b = ty[i], c = tz[i];
+    ox[i] = (float)(Rt[0] * a + Rt[1] * b + Rt[2] * c + Rt[9]);
+    oy[i] = (float)(Rt[3] * a + Rt[4] * b + Rt[5] * c + Rt[10]);
+    oz[i] = (float)(Rt[6] * a + Rt[7] * b + Rt[8] * c + Rt[11]);
+}
+
+__global__ void __launch_bounds__(512) reg_flat_solve_kernel(FlatModel m, const double* __restrict__ acc, int solver,
+                                                             double* __restrict__ Rt, double* __restrict__ q_hist,
+                                                             double* __restrict__ qstate, int* __restrict__ ctrl, float tol) {
+    if (ctrl[0]) return;
+    __shared__ double sm[16 * kSys];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const double f32eps = 1.1920928955078125e-07;
+    if (solver == HGMM_SOLVER_TWIST_LSTSQ) {
+        double v[kSys];
+        for (int k = 0; k < kSys; ++k) v[k] = 0.0;
+        for (int j = tid; j < m.J; j += nth) {
+            const double* A = acc + kAccHdr + (size_t)j * kMom;
+            const double M0 = A[0];
+            if (M0 < f32eps) continue;
+            const float* c = m.covs + 9 * (size_t)j;
+            Sym3 sg{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
+            const double det = sym3_det(sg);
+            if (!(det > 0.0)) continue;
+            const Sym3 ad = sym3_adj(sg);
+            const double r = 1.0 / det;
+            const double P[3][3] = {{ad.xx * r, ad.xy * r, ad.xz * r}, {ad.xy * r, ad.yy * r, ad.yz * r}, {ad.xz * r, ad.yz * r, ad.zz * r}};
+            const double mx = m.means[3 * j], my = m.means[3 * j + 1], mz = m.means[3 * j + 2];
+            const double rr[3] = {-A[1] / M0, -A[2] / M0, -A[3] / M0};              // mu - s = -S1/S0
+            const double sx = mx - rr[0], sy = my - rr[1], sz = mz - rr[2];
+            const double Jm[3][6] = {{0, sz, -sy, 1, 0, 0}, {-sz, 0, sx, 0, 1, 0}, {sy, -sx, 0, 0, 0, 1}};
+            double PJ[3][6];
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 6; ++b) PJ[a][b] = P[a][0] * Jm[0][b] + P[a][1] * Jm[1][b] + P[a][2] * Jm[2][b];
+            int k = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b) v[k++] += M0 * (Jm[0][a] * PJ[0][b] + Jm[1][a] * PJ[1][b] + Jm[2][a] * PJ[2][b]);
+            const double Pr[3] = {P[0][0] * rr[0] + P[0][1] * rr[1] + P[0][2] * rr[2], P[1][0] * rr[0] + P[1][1] * rr[1] + P[1][2] * rr[2],
+                                  P[2][0] * rr[0] + P[2][1] * rr[1] + P[2][2] * rr[2]};
+            for (int a = 0; a < 6; ++a) v[21 + a] += M0 * (Jm[0][a] * Pr[0] + Jm[1][a] * Pr[1] + Jm[2][a] * Pr[2]);
+            v[27] += M0 * (rr[0] * Pr[0] + rr[1] * Pr[1] + rr[2] * Pr[2]);
         }
+        block_reduce<kSys>(v, sm, tid, nth);
+        if (tid == 0) twist_finish(sm, Rt, q_hist, qstate, ctrl, tol);
+    } else {
+        double v[kPro];
+        for (int k = 0; k < kPro; ++k) v[k] = 0.0;
+        for (int j = tid; j < m.J; j += nth) {
+            const double* A = acc + kAccHdr + (size_t)j * kMom;
+            const double w = A[0];
+            if (w < f32eps) continue;
+            const double mu[3] = {m.means[3 * j], m.means[3 * j + 1], m.means[3 * j + 2]};
+            const double sc[3] = {mu[0] + A[1] / w, mu[1] + A[2] / w, mu[2] + A[3] / w};
+            v[0] += w;
+            for (int a = 0; a < 3; ++a) {
+                v[1 + a] += w * sc[a];
+                v[4 + a] += w * mu[a];
+                for (int b = 0; b < 3; ++b) v[7 + 3 * a + b] += w * sc[a] * mu[b];
+            }
+            v[16] += w * (sc[0] * sc[0] + sc[1] * sc[1] + sc[2] * sc[2]);
+            v[17] += w * (mu[0] * mu[0] + mu[1] * mu[1] + mu[2] * mu[2]);
+        }
+        block_reduce<kPro>(v, sm, tid, nth);
+        if (tid == 0) procrustes_finish(sm, Rt, q_hist, qstate, ctrl, tol);
     }
 }
 
@@ -557,6 +654,18 @@ cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, 
 cudaError_t launch_reg_solve(const TreeModel& t, double* racc, int zero_after, int solver, double* Rt, double* q_hist,
                              double* qstate, int* ctrl, float tol, cudaStream_t s) {
     reg_solve_kernel<<<1, 512, 0, s>>>(t, racc, zero_after, solver, Rt, q_hist, qstate, ctrl, tol);
+    return cudaGetLastError();
+}
+
+void launch_transform_soa(const float* tx, const float* ty, const float* tz, int n, const double* Rt, float* ox, float* oy, float* oz,
+                          const int* ctrl, cudaStream_t s) {
+    if (n <= 0) return;
+    transform_soa_kernel<<<(n + 255) / 256, 256, 0, s>>>(tx, ty, tz, n, Rt, ox, oy, oz, ctrl);
+}
+
+cudaError_t launch_reg_flat_solve(const FlatModel& m, const double* acc, int solver, double* Rt, double* q_hist, double* qstate,
+                                  int* ctrl, float tol, cudaStream_t s) {
+    reg_flat_solve_kernel<<<1, 512, 0, s>>>(m, acc, solver, Rt, q_hist, qstate, ctrl, tol);
     return cudaGetLastError();
 }
 

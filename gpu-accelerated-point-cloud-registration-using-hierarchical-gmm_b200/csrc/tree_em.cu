@@ -417,15 +417,12 @@ __global__ void tree_mstep_kernel(TreeModel t, int lb, int count, double* __rest
     tree_mstep_node(t, lb, local, acc, n_total, ld);
 }
 
-// moments of node `local` of the level -> parameters (mlEstimator, hgmm_cupy_cpu_working.py:109-119), re-packed; moments cleared
-__device__ void tree_mstep_node(const TreeModel& t, int lb, int local, double* __restrict__ acc, double n_total, float ld) {
+// centred moments A of node `local` of the level -> parameters (mlEstimator, hgmm_cupy_cpu_working.py:109-119: blank node if
+// M0 < ld), written to the model and returned packed
+__device__ __forceinline__ PackedComp tree_mstep_apply(const TreeModel& t, int lb, int local, const double* A, double n_total, float ld) {
     const int j = lb + local;
-    double* Ag = acc + kAccHdr + (size_t)local * kMom;
-    double A[kMom];
-#pragma unroll
-    for (int k = 0; k < kMom; ++k) A[k] = __ldcg(Ag + k);
     const double M0 = A[0];
-    // mlEstimator (hgmm_cupy_cpu_working.py:109-119): blank node if M0 < ld
+    PackedComp pc;
     if (M0 >= (double)ld) {
         const double r = 1.0 / M0;
         const double dx = A[1] * r, dy = A[2] * r, dz = A[3] * r;
@@ -439,81 +436,31 @@ __device__ void tree_mstep_node(const TreeModel& t, int lb, int local, double* _
         float* c = t.cov + 9 * j;
         c[0] = (float)s.xx; c[1] = c[3] = (float)s.xy; c[2] = c[6] = (float)s.xz;
         c[4] = (float)s.yy; c[5] = c[7] = (float)s.yz; c[8] = (float)s.zz;
-        t.packed[j] = pack_full(log(w), fx, fy, fz, s, false, 1e-15);
+        pc = pack_full(log(w), fx, fy, fz, s, false, 1e-15);
     } else {
         t.pi[j] = 0.f;
         t.mu[3 * j] = t.mu[3 * j + 1] = t.mu[3 * j + 2] = 0.f;
         float* c = t.cov + 9 * j;
         c[0] = c[4] = c[8] = 1.f;
         c[1] = c[2] = c[3] = c[5] = c[6] = c[7] = 0.f;
-        t.packed[j] = pack_full(-INFINITY, 0, 0, 0, Sym3{1, 0, 0, 1, 0, 1}, false, 1e-15);
+        pc = pack_full(-INFINITY, 0, 0, 0, Sym3{1, 0, 0, 1, 0, 1}, false, 1e-15);
     }
+    t.packed[j] = pc;
+    return pc;
+}
+
+// moments of node `local` of the level (in acc) -> parameters; moments cleared
+__device__ void tree_mstep_node(const TreeModel& t, int lb, int local, double* __restrict__ acc, double n_total, float ld) {
+    double* Ag = acc + kAccHdr + (size_t)local * kMom;
+    double A[kMom];
+#pragma unroll
+    for (int k = 0; k < kMom; ++k) A[k] = __ldcg(Ag + k);
+    tree_mstep_apply(t, lb, local, A, n_total, ld);
 #pragma unroll
     for (int k = 0; k < kMom; ++k) Ag[k] = 0.0;
 }
 
-// ------------------------------------------------------------------------------------------
-// Persistent level kernel (DRAFT: compiled, not yet run on a GPU -- selected only by HGMM_TREE_PERSIST=1, single rank,
-// HGMM_LL_ESTEP).  The two-kernel iteration costs ~17 us for ~3 us of arithmetic: here one cooperative launch
-// runs the whole EM loop of a level -- E-step over a grid-stride loop of 8-chunk groups, grid barrier, M-step spread over every
-// thread of the grid + the stopping rule by thread 0, grid barrier -- so an iteration costs two grid barriers instead of two
-// launch boundaries and no flag ever travels to the host.
-// gbar: [0] arrival counter, [1] generation.  All CTAs are co-resident (cudaLaunchCooperativeKernel).
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned* gbar, unsigned nblocks) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        volatile unsigned* vb = gbar;
-        const unsigned gen = vb[1];
-        __threadfence();                                   // this CTA's writes are visible before it counts as arrived
-        if (atomicAdd(gbar, 1u) == nblocks - 1) {
-            vb[0] = 0u;
-            __threadfence();
-            atomicAdd(gbar + 1, 1u);                       // release the generation
-        } else {
-            while (vb[1] == gen) {}
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(256, 3) tree_level_kernel(const float* __restrict__ px, const float* __restrict__ py,
-                                                            const float* __restrict__ pz, const int* __restrict__ chunk_parent,
-                                                            const int* __restrict__ chunk_start, const int* __restrict__ chunk_len,
-                                                            const int* __restrict__ n_chunks_dev, TreeModel t, int lb, int count,
-                                                            double* __restrict__ acc, uint8_t* __restrict__ slot, double n_total,
-                                                            float ld, float ls, int max_iters, int* __restrict__ ctrl,
-                                                            double* __restrict__ qstate, unsigned* __restrict__ gbar) {
-    __shared__ float s_part[8][8 * kMom];
-    __shared__ int s_parent[8];
-    __shared__ double s_ll[8];
-    const int n_chunks = *n_chunks_dev;
-    const int n_groups = (n_chunks + 7) / 8;
-    const PackedComp* packed_level = t.packed + lb;
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-    for (int it = 0; it < max_iters; ++it) {
-        for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-            tree_estep2_group(px, py, pz, chunk_parent, chunk_start, chunk_len, n_chunks, packed_level, acc, slot, g, s_part, s_parent,
-                              s_ll);
-            __syncthreads();                               // s_part / s_parent / s_ll are reused by the next group
-        }
-        grid_barrier(gbar, gridDim.x);                     // every moment and the log-likelihood sum have landed in acc
-        if (gtid == 0) {                                   // stopping rule of tree_mstep_kernel (merge_converge branch)
-            const double q = __ldcg(acc);
-            acc[0] = 0.0;
-            const int n_it = it + 1;
-            ctrl[1] = n_it;
-            qstate[1] = q;
-            const bool conv = fabs(q - __ldcg(qstate)) < (double)ls || n_it >= max_iters;
-            qstate[0] = q;
-            ctrl[0] = conv ? 1 : 0;
-        }
-        for (int local = gtid; local < count; local += gthreads) tree_mstep_node(t, lb, local, acc, n_total, ld);
-        grid_barrier(gbar, gridDim.x);                     // new parameters and the verdict are visible everywhere
-        if (__ldcg(ctrl) != 0) break;
-    }
-}
+#include "tree_level.cuh"
 
 // |q - prevQ| < ls with prevQ = 0 at level start (hgmm_gpu.py:520,533-535).  qstate: [0] prevQ, [1] last q.
 __global__ void tree_converge_kernel(double* __restrict__ acc, int* __restrict__ ctrl, int* __restrict__ done_at, int it,
@@ -803,26 +750,61 @@ void launch_tree_mstep(const TreeModel& t, int level, double* acc, double n_tota
                        ls, max_iters, (volatile int*)prog);
 }
 
-// one cooperative launch for the whole EM loop of a level; returns cudaErrorNotSupported when the device cannot co-schedule
-cudaError_t launch_tree_level(const TreeWork& w, const TreeModel& t, int level, double* acc, int n_chunks_bound,
+// shared-memory plan of tree_level_kernel for a rank holding n points: the warps' parameter blocks, the fold stage, the chunk
+// descriptors, and as many resident points as the rest holds
+void tree_level_plan(int n, int chunk_points, int level, int num_sms, int smem_optin, int* pt_cap, int* chunk_cap, int* stage_cap,
+                     size_t* smem_bytes) {
+    const int per_cta = (n + num_sms - 1) / num_sms + chunk_points + 64;          // balanced by points, whole chunks
+    const long long parents = level == 0 ? 1 : (long long)level_count(level - 1);
+    const int sc = 96;                                                            // parked fold results (320 B each)
+    long long cc = per_cta / chunk_points + (parents + num_sms - 1) / num_sms + 16;      // chunk descriptors kept on chip
+    if (cc > 4096) cc = 4096;
+    const long long fixed = (long long)(kTlThreads / 32) * 320 + (long long)sc * 324 + cc * 12;
+    const long long room = (long long)smem_optin - fixed - 4096;                  // static shared memory of the kernel + slack
+    int pc = per_cta;
+    if ((long long)pc * 12 > room) pc = 0;                                        // does not fit: stream the points from L2 / HBM
+    *pt_cap = pc;
+    *chunk_cap = (int)cc;
+    *stage_cap = sc;
+    *smem_bytes = (size_t)fixed + (size_t)pc * 12;
+}
+
+// one cooperative launch for the whole EM loop of a level (tree_level.cuh)
+cudaError_t launch_tree_level(const TreeWork& w, const TreeModel& t, int level, int n, double* acc, size_t acc_stride,
                               const int* n_chunks_dev, double n_total, float ld, float ls, int max_iters, int* ctrl, double* qstate,
-                              unsigned* gbar, int num_sms, cudaStream_t s) {
+                              unsigned* gbar, int chunk_points, const TreeXchgHost& xh, int num_sms, long long* prof,
+                              cudaStream_t s) {
+    TreeLevelArgs a;
+    a.prof = prof;
+    a.px = w.x; a.py = w.y; a.pz = w.z;
+    a.chunk_parent = w.chunk_parent; a.chunk_start = w.chunk_start; a.chunk_len = w.chunk_len; a.n_chunks_dev = n_chunks_dev;
+    a.slot = w.slot;
+    a.t = t;
+    a.lb = level_base(level); a.cnt = level_count(level); a.n = n;
+    a.acc = acc; a.acc_stride = acc_stride;
+    a.n_total = n_total; a.ld = ld; a.ls = ls; a.max_iters = max_iters;
+    a.ctrl = ctrl; a.qstate = qstate; a.gbar = gbar;
+    for (int r = 0; r < kXchgMaxRanks; ++r) {
+        a.x.pk[r] = reinterpret_cast<unsigned long long*>(xh.pk[r]);
+        a.x.fin[r] = reinterpret_cast<unsigned long long*>(xh.fin[r]);
+        a.x.mom[r] = reinterpret_cast<uint4*>(xh.mom[r]);
+        a.x.ll[r] = reinterpret_cast<uint4*>(xh.ll[r]);
+    }
+    a.x.rank = xh.rank; a.x.nranks = xh.nranks; a.x.base = xh.base; a.x.mom_cap = xh.mom_cap; a.x.timeout_ns = xh.timeout_ns;
+    const int smem_optin = device_smem_optin();
+    size_t smem = 0;
+    tree_level_plan(n, chunk_points, level, num_sms, smem_optin, &a.pt_cap, &a.chunk_cap, &a.stage_cap, &smem);
+    static DeviceOnce once;
+    if (once.first()) {
+        cudaError_t e = cudaFuncSetAttribute(tree_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096);
+        if (e != cudaSuccess) return e;
+    }
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tree_level_kernel, 256, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tree_level_kernel, kTlThreads, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorNotSupported;
-    int grid = (n_chunks_bound + 7) / 8;
-    const int cap = occ * num_sms;
-    if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
-    const float *px = w.x, *py = w.y, *pz = w.z;
-    const int *cpar = w.chunk_parent, *cst = w.chunk_start, *cln = w.chunk_len;
-    TreeModel tm = t;
-    int lb = level_base(level), cnt = level_count(level);
-    uint8_t* slot = w.slot;
-    void* args[] = {&px, &py, &pz, &cpar, &cst, &cln, &n_chunks_dev, &tm, &lb, &cnt, &acc, &slot, &n_total, &ld, &ls, &max_iters,
-                    &ctrl, &qstate, &gbar};
-    return cudaLaunchCooperativeKernel((const void*)tree_level_kernel, dim3(grid), dim3(256), args, 0, s);
+    void* args[] = {(void*)&a};
+    return cudaLaunchCooperativeKernel((const void*)tree_level_kernel, dim3(num_sms), dim3(kTlThreads), args, smem, s);
 }
 
 void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, int* prog,

@@ -19,7 +19,8 @@
 // waiting for it, so no co-scheduling is needed.  Every rank adds the contributions in rank order 0..R-1 (its own from
 // registers): replicas stay bit-identical.  A rank is at most one epoch ahead of any other (its next push needs their
 // previous one), hence two parities suffice.
-// The poll has a clock64() deadline; on expiry ctrl[7] is set and the host reports HGMM_ERR_NCCL instead of hanging.
+// The poll has a %globaltimer deadline (HGMM_XCHG_TIMEOUT_S, default 30 s); on expiry ctrl[7] is set, every CTA that sees it
+// leaves without finalizing, and the host reports HGMM_ERR_NCCL instead of hanging.
 __device__ __forceinline__ void xchg_put(uint4* cell, double v, uint32_t epoch) {
     const unsigned long long u = (unsigned long long)__double_as_longlong(v);
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(cell), "r"((uint32_t)u), "r"(epoch) : "memory");
@@ -28,8 +29,10 @@ __device__ __forceinline__ void xchg_put(uint4* cell, double v, uint32_t epoch) 
 }
 // one peer's contribution for this lane's component: all 12 cells are loaded together (independent loads, ONE L2 round
 // trip when the data has arrived) and re-polled until every word carries the epoch.  false on timeout.
-__device__ __forceinline__ bool xchg_get_row(const uint4* src, size_t Jp, int j, int b, bool hdr_lane, uint32_t epoch, double* v) {
-    const long long t0 = clock64();
+__device__ __forceinline__ bool xchg_get_row(const uint4* src, size_t Jp, int j, int b, bool hdr_lane, uint32_t epoch, double* v,
+                                             unsigned long long timeout_ns, const int* ctrl) {
+    unsigned long long t0 = 0ull;
+    unsigned spins = 0;
     for (;;) {
         uint4 c[kMom + 2];
 #pragma unroll
@@ -55,7 +58,14 @@ __device__ __forceinline__ bool xchg_get_row(const uint4* src, size_t Jp, int j,
             for (int k = 0; k < kMom + 2; ++k) v[k] = __longlong_as_double((long long)(((unsigned long long)c[k].z << 32) | c[k].x));
             return true;
         }
-        if (clock64() - t0 > 6000000000LL) return false;     // ~3 s: a peer died or the ranks' call sequences diverged
+        if ((++spins & 255u) == 0u) {                          // deadline (XchgView::timeout_ns, default 30 s): a peer died or the
+            unsigned long long now;                            // ranks' call sequences diverged; another CTA's verdict ends the wait too
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0ull) t0 = now;
+            int bad;
+            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(bad) : "l"(ctrl + 7) : "memory");
+            if (bad || now - t0 > timeout_ns) return false;
+        }
     }
 }
 
@@ -139,16 +149,20 @@ __global__ void __launch_bounds__(512) flat_reduce_exchange_finalize_kernel(Flat
     // ---------------- warp r collects rank r's contribution from this rank's own window (all peers polled in parallel)
     if (w < R && w != me) {
         double v[kMom + 2];
-        const bool ok = xchg_get_row(xc.data[me] + par_off + (size_t)w * slot, (size_t)m.Jp, j, b, lane == 0, epoch, v);
-        if (!ok) s_bad = 1;
+        const bool ok = xchg_get_row(xc.data[me] + par_off + (size_t)w * slot, (size_t)m.Jp, j, b, lane == 0, epoch, v, xc.timeout_ns, ctrl);
+        if (!ok) {
+            s_bad = 1;
+            atomicExch(ctrl + 7, 1);     // the other CTAs of the grid stop waiting and skip their finalize as well
+        }
 #pragma unroll
         for (int k = 0; k < kMom + 2; ++k) xs[w][k][lane] = v[k];
     }
     __syncthreads();
     if (w != 0) return;
-    if (s_bad) {
-        if (lane == 0) ctrl[7] = 1;
-        return;
+    {
+        int bad;
+        asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(bad) : "l"(ctrl + 7) : "memory");
+        if (s_bad || bad) return;        // no CTA that has seen the failure updates its components (best effort across CTAs)
     }
     // ---------------- add the ranks' contributions in rank order (own from registers)
     {

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhgmm.so")
+LIB_PATH = os.environ.get("HGMM_LIB_PATH") or os.path.join(_HERE, "libhgmm.so")      # override: A/B builds of the library
 
 HGMM_OK = 0
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -52,6 +52,7 @@ SIGNATURES = {
     "hgmm_launch_count": (C.c_int64, [_VP]),
     "hgmm_set_points": (C.c_int, [_VP, _VP, C.c_int64, C.c_int]),
     "hgmm_total_points": (C.c_int64, [_VP]),
+    "hgmm_declare_total_points": (C.c_int, [_VP, C.c_int64]),
     "hgmm_fit_flat": (C.c_int, [_VP, C.POINTER(FlatConfig), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "hgmm_predict_flat": (C.c_int, [_VP, _VP, C.c_int64, C.c_int, _VP]),
     "hgmm_tree_total_nodes": (C.c_int64, [C.c_int32]),
@@ -61,6 +62,7 @@ SIGNATURES = {
     "hgmm_reg_estep": (C.c_int, [_VP, _VP, _VP, C.c_float, _VP, _VP, _VP]),
     "hgmm_reg_mstep": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP]),
     "hgmm_register_tree": (C.c_int, [_VP, C.POINTER(RegConfig), _VP, _VP, _VP, _VP, _VP]),
+    "hgmm_register_flat": (C.c_int, [_VP, C.POINTER(RegConfig), _VP, _VP, _VP, _VP, _VP]),
     "hgmm_l2_set_mixtures": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP, _VP, C.c_int32]),
     "hgmm_l2_cost_grad": (C.c_int, [_VP, _VP, C.c_double, _VP, _VP]),
     "hgmm_l2_optimize": (C.c_int, [_VP, _VP, C.c_double, C.c_int32, C.c_double, _VP, _VP, _VP, _VP]),

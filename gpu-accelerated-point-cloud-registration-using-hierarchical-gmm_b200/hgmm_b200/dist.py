@@ -69,7 +69,20 @@ def attach_communicator(engine, p2p=None):
     engine.comm_init(rank, world, uid)
     if p2p is None:
         p2p = os.environ.get("HGMM_NO_P2P", "0") != "1"
-    if p2p and 2 <= world <= 8:
+    if p2p:
+        attach_p2p(engine)
+    return rank, world
+
+
+def attach_p2p(engine):
+    """(re)create the peer-memory exchange windows of every rank of the default process group (collective); returns True when
+    every rank is attached, else all of them stay on / fall back to NCCL.  Usable again after Engine.p2p_detach()."""
+    import torch
+    import torch.distributed as dist
+    from ._lib import HgmmError
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ok = False
+    if 2 <= world <= 8:
         try:
             handle = engine.p2p_export()
         except HgmmError:
@@ -89,7 +102,10 @@ def attach_communicator(engine, p2p=None):
             ok = _p2p_self_test(engine, rank, world, dev)
         if not ok and engine.p2p_enabled:
             engine.p2p_detach()
-    return rank, world
+    return ok
+
+
+reattach_p2p = attach_p2p
 
 
 def _p2p_self_test(engine, rank, world, dev):
@@ -107,6 +123,7 @@ def _p2p_self_test(engine, rank, world, dev):
     w0 = np.full(J, 1.0 / J, np.float32)
     good, digest = 1, np.zeros(4, np.float64)
     try:
+        engine.declare_total_points(0)       # the toy cloud's total comes from the all-reduce, whatever was declared before
         engine.set_points(pts)
         r = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=2)
         digest = np.array([r["means"].astype(np.float64).sum(), r["covs"].astype(np.float64).sum(),

@@ -21,8 +21,10 @@ class Engine:
         if rc != L.HGMM_OK or not self._ctx:
             raise L.HgmmError("hgmm_create failed (status %d): no usable CUDA device %d -- libhgmm has no CPU path" % (rc, device))
         self.device = int(device)
-        self._keep = []
+        self._stream = int(stream) if stream else None
         self.n_points = 0
+        self.model_token = None       # who installed the tree / target last (GMMTree instances share engines safely through it)
+        self.target_token = None
 
     # -- plumbing ----------------------------------------------------------------------------
     def close(self):
@@ -70,6 +72,9 @@ class Engine:
             t = points
             if t.dim() != 2 or t.shape[1] != 3 or str(t.dtype) != "torch.float32" or not t.is_contiguous():
                 raise ValueError("device clouds must be contiguous float32 [N,3]")
+            # libhgmm reads the tensor on ITS stream: the stream that produced it must be done first (include/hgmm.h)
+            import torch
+            torch.cuda.current_stream(t.device).synchronize()
             return C.c_void_p(t.data_ptr()), int(t.shape[0]), L.MEM_DEVICE, t
         if hasattr(points, "is_pinned") and hasattr(points, "numpy"):      # CPU torch tensor (possibly pinned)
             t = points
@@ -83,11 +88,19 @@ class Engine:
         return L.ptr(a), int(a.shape[0]), L.MEM_HOST, a
 
     # -- data --------------------------------------------------------------------------------
-    def set_points(self, points):
+    def set_points(self, points, total=None):
+        """`total` (multi-GPU): the number of points over all ranks when the caller knows it -- skips the all-reduce."""
         p, n, kind, keep = self._cloud_arg(points)
+        if total is not None:
+            self.declare_total_points(total)
         self._check(self._lib.hgmm_set_points(self._ctx, p, n, kind), "hgmm_set_points")
+        self._src_keep = keep         # a pinned host tensor is read asynchronously: hold it until the next cloud replaces it
         self.n_points = n
+        self.model_token = None
         return self
+
+    def declare_total_points(self, total):
+        self._check(self._lib.hgmm_declare_total_points(self._ctx, int(total)), "hgmm_declare_total_points")
 
     # -- flat mixture ------------------------------------------------------------------------
     def fit_flat(self, means, covs, weights, cov_type="full", flavor=None, max_iter=10, tol=0.0, sigma_bug=False,
@@ -145,6 +158,7 @@ class Engine:
         rc = self._lib.hgmm_fit_tree(self._ctx, C.byref(cfg), L.ptr(init_means), L.ptr(pi), L.ptr(mu), L.ptr(cov), L.ptr(cur),
                                      L.ptr(iters), L.ptr(q))
         self._check(rc, "hgmm_fit_tree")
+        self.model_token = None
         return {"pi": pi, "mu": mu, "cov": cov, "current": cur, "iters": iters, "q": q}
 
     def tree_set_model(self, max_level, pi, mu, cov):
@@ -152,12 +166,15 @@ class Engine:
         pi, mu, cov = L.f32c(pi, (nt,)), L.f32c(mu, (nt, 3)), L.f32c(cov, (nt, 3, 3))
         self._check(self._lib.hgmm_tree_set_model(self._ctx, int(max_level), L.ptr(pi), L.ptr(mu), L.ptr(cov)), "hgmm_tree_set_model")
         self._tree_level = int(max_level)
+        self.model_token = None
         return self
 
     # -- registration ------------------------------------------------------------------------
     def reg_set_target(self, target):
         p, n, kind, keep = self._cloud_arg(target)
         self._check(self._lib.hgmm_reg_set_target(self._ctx, p, n, kind), "hgmm_reg_set_target")
+        self._tgt_keep = keep
+        self.target_token = None
         return self
 
     def reg_estep(self, rot, t, lambda_c, nt, want_m2=True):
@@ -187,6 +204,19 @@ class Engine:
         hist = np.zeros(int(maxiter))
         rc = self._lib.hgmm_register_tree(self._ctx, C.byref(cfg), L.ptr(rot), L.ptr(t), L.ptr(q), L.ptr(it), L.ptr(hist))
         self._check(rc, "hgmm_register_tree")
+        return rot, t, float(q[0]), int(it[0]), hist[:int(it[0])]
+
+    def register_flat(self, rot=None, t=None, solver="procrustes_svd", maxiter=20, tol=1.0e-4):
+        """registration of the target against the flat mixture of the last fit_flat -> (rot, t, q, iterations, q history);
+        (rot, t) is the FORWARD transform (target -> model frame), like register_tree"""
+        rot = np.identity(3) if rot is None else np.array(rot, np.float64).reshape(3, 3).copy()
+        t = np.zeros(3) if t is None else np.array(t, np.float64).reshape(3).copy()
+        cfg = L.RegConfig(L.SOLVERS[solver], int(maxiter), float(tol), 0.0)
+        q = np.zeros(1)
+        it = np.zeros(1, np.int32)
+        hist = np.zeros(int(maxiter))
+        rc = self._lib.hgmm_register_flat(self._ctx, C.byref(cfg), L.ptr(rot), L.ptr(t), L.ptr(q), L.ptr(it), L.ptr(hist))
+        self._check(rc, "hgmm_register_flat")
         return rot, t, float(q[0]), int(it[0]), hist[:int(it[0])]
 
     # -- L2 registration of two flat mixtures ---------------------------------------------------

@@ -108,33 +108,49 @@ class GMMTree():
         self._tf_result = self._tf_type()
         self._callbacks = []
         self._engine = engine or default_engine()
-        self._target_id = None
+        self._target = None           # the array last uploaded as target (a reference is kept: `is` cannot alias a freed object)
         if source is not None:
             self.set_source(source)
 
+    # The reference keeps the model per GMMTree object (hgmm_gpu.py:685-706).  Here the device copy lives in an Engine that other
+    # GMMTree / buildGMMTree / predict calls may share: the host copy of the model is the object's own, and `model_token` /
+    # `target_token` on the engine say who installed the device copy last -- anyone else re-installs before using it.
     def set_source(self, source):
         self._source = _cloud(source)
         self._mixingCoeff, self._mean, self._covar = buildGMMTree(self._source, self._tree_level, self._ls, self._ld,
                                                                   sig2=self._sig2, ll_mode=self._ll_mode, engine=self._engine)
+        self._engine.model_token = self
 
     def set_model(self, mixingCoeff, mean, covar):
         """install an existing tree instead of building one"""
         self._mixingCoeff, self._mean, self._covar = (np.asarray(mixingCoeff), np.asarray(mean), np.asarray(covar))
         self._engine.tree_set_model(self._tree_level, self._mixingCoeff, self._mean, self._covar)
+        self._engine.model_token = self
 
     def set_callbacks(self, callbacks):
         self._callbacks = callbacks
 
+    def _ensure_model(self):
+        if self._engine.model_token is not self:
+            self._engine.tree_set_model(self._tree_level, self._mixingCoeff, self._mean, self._covar)
+            self._engine.model_token = self
+
     def _ensure_target(self, target):
-        key = (id(target), getattr(target, "shape", None))
-        if key != self._target_id:
+        """upload unless this very object uploaded this very array last (pass a copy, or call `invalidate_target()`, after
+        mutating an array in place)"""
+        if self._engine.target_token is not self or self._target is not target:
             self._engine.reg_set_target(target)
-            self._target_id = key
+            self._engine.target_token = self
+            self._target = target
+
+    def invalidate_target(self):
+        self._target = None
 
     def expectation_step(self, target):
         """hgmm_gpu.py:722-727: `target` is the ALREADY transformed cloud."""
+        self._ensure_model()
         self._engine.reg_set_target(_cloud(target))
-        self._target_id = None
+        self._target = None
         m0, m1, m2 = self._engine.reg_estep(np.identity(3), np.zeros(3), self._lambda_c, len(self._mixingCoeff))
         return EstepResult(m0, m1, m2)
 
@@ -147,6 +163,7 @@ class GMMTree():
         """hgmm_gpu.py:754-768: iterate on the device from the current `_tf_result`; returns the
         inverse transform and the last q, like the reference."""
         tgt = _cloud(target)
+        self._ensure_model()
         self._ensure_target(tgt)
         if self._callbacks:
             # per-iteration callbacks need the host in the loop

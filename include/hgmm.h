@@ -14,7 +14,7 @@
  *   hgmm_reg_estep         gmmTreeRegESTep                   src/python/hgmm/hgmm_gpu.py:550-577
  *   hgmm_reg_mstep         GMMTree.maximization_step         src/python/hgmm/hgmm_gpu.py:729-752
  *   hgmm_register_tree     GMMTree.registration              src/python/hgmm/hgmm_gpu.py:754-768
- *                          GMMRegistration::pointCloudRegisterGPU (empty stub) gmm_reg.cu:54-56
+ *   hgmm_register_flat     GMMRegistration::pointCloudRegisterGPU (empty stub) src/c++/gmm_registration/gmm_reg.cu:54-56
  *   hgmm_io_read_ply/pcd   readData  src/c++/main.cpp:45-79, readPointCloud  src/c++/main_reg.cpp:106-161
  *   hgmm_l2_*              RigidCostFunction / L2DistRegistration  src/python/gmmreg_gpu/cost_functions.py:29-69, gmmreg.py:62-121
  *   hgmm_fill_vbo          scanRegistration::copyBoidsToVBO  src/c++/gmm_fit/gmm_kernels.cu:532-542
@@ -112,10 +112,17 @@ const char* hgmm_version(void);
 int64_t hgmm_launch_count(const hgmm_ctx* ctx);
 
 /* ---- data ---- */
-/* The cloud the mixture is fitted to (this rank's shard when a communicator is attached). */
+/* The cloud the mixture is fitted to (this rank's shard when a communicator is attached).  DEVICE and pageable HOST buffers are
+ * consumed before the call returns; a PINNED host buffer is read asynchronously and must stay untouched until the next call
+ * that synchronises (any fit / predict / register).  HGMM_MEM_DEVICE input is read on the context's stream: the caller must have finished writing it (synchronise
+ * the producing stream, or create the context on that stream) -- the Python wrapper does this for torch tensors. */
 int hgmm_set_points(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind);
 /* total number of points over all ranks (= n without a communicator) */
 int64_t hgmm_total_points(const hgmm_ctx* ctx);
+/* With a communicator hgmm_set_points all-reduces the shard sizes (a blocking collective).  A caller that sharded the cloud itself
+ * knows the total: declaring it (> 0) makes every following hgmm_set_points local; 0 restores the all-reduce.  Every rank must
+ * declare the same value. */
+int hgmm_declare_total_points(hgmm_ctx* ctx, int64_t n_total);
 
 /* ---- flat mixture ---- */
 /* init_means [J,3]; init_covs: FULL [J,9] | DIAG [J,3] | SPHERICAL [J] (variances); init_weights [J].
@@ -154,6 +161,16 @@ int hgmm_reg_mstep(hgmm_ctx* ctx, int32_t solver, double* rot, double* t, double
  * maps target onto the model (the reference returns its inverse, hgmm_gpu.py:768 -- the Python
  * wrapper inverts). out_q_hist [maxiter] may be NULL. */
 int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, double* t,
+                       double* out_q, int32_t* out_iters, double* out_q_hist);
+
+/* ---- registration against the context's FLAT mixture (BASELINE configs[3]: "GMM registration, J components, weighted-SVD solve") ----
+ * replaces GMMRegistration::pointCloudRegisterGPU  src/c++/gmm_registration/gmm_reg.cu:54-56 (an empty stub in the reference;
+ * class fields gmm_reg.h:8-20).  Model = the mixture of the last hgmm_fit_flat (fitted to the context's points), target =
+ * hgmm_reg_set_target.  Each iteration: responsibilities of the transformed target over all J components (the fit's own fused
+ * sweep), then HGMM_SOLVER_PROCRUSTES (weighted Procrustes between the mass centroids and the means, 3x3 Jacobi SVD; any
+ * covariance type) or HGMM_SOLVER_TWIST_LSTSQ (the tree solver's linearised Mahalanobis step; full covariances).  rot/t, q,
+ * iterations and the stopping rule are those of hgmm_register_tree; lambda_c is ignored. */
+int hgmm_register_flat(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, double* t,
                        double* out_q, int32_t* out_iters, double* out_q_hist);
 
 /* ---- L2-distance registration of two flat mixtures (float64) ----

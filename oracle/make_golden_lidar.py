@@ -38,11 +38,18 @@ def c5_subsample():
     return P[perm[:C5_SUB]]
 
 
-def run(tag, P, L, mode, sig2=4.0, ls=20.0, ld=1e-4):
+def run(tag, P, L, mode, sig2=4.0, ls=20.0, ld=1e-4, fixed_iters=None):
+    """fixed_iters: exactly that many EM iterations per level (ls = 0 never fires: |q - prevQ| < 0) -- the stopping rule
+    |q - prevQ| < 20 sits on a plateau of the log-likelihood at these sizes, so WHICH iteration crosses it depends on the last
+    bits of q (summation order); a fixed count gives a fixture every implementation can be held to at 1e-4."""
     init = P[hgmm_tree.reference_init_indices(L)]
     t0 = time.time()
+    if fixed_iters:
+        ls = 0.0
+        mode = mode + "_fixed%d" % fixed_iters
     pi, mu, cov, cur, iters, trace = hgmm_tree.build_gmm_tree(P, L, ls, ld, init.astype(np.float64), sig2=np.float32(sig2),
-                                                             ll_mode=mode, return_trace=True)
+                                                             ll_mode=mode.split("_")[0], return_trace=True,
+                                                             max_iters_per_level=fixed_iters or 10000)
     dt = time.time() - t0
     print("%s[%s]: %d points, L=%d: iterations %s, %.1f s of oracle time" % (tag, mode, len(P), L, iters, dt), flush=True)
     lb = hgmm_tree.level(L - 1)
@@ -60,6 +67,14 @@ def main():
         run("lidar100k_L4", c3_cloud(), 4, "estep")
     elif what == "c3_level":
         run("lidar100k_L4", c3_cloud(), 4, "level")
+    elif what == "fixed":
+        run("lidar100k_L4", c3_cloud(), 4, "estep", fixed_iters=12)
+        run("lidar50k_L5", c5_subsample(), 5, "estep", fixed_iters=10)
+    elif what == "fixed2":
+        # two iterations per level: every level's E-step / M-step / partition is exercised at config size while the fp32-vs-fp64
+        # differences have had no time to be amplified through the hard hand-offs (tests/test_gpu_parity.py explains)
+        run("lidar100k_L4", c3_cloud(), 4, "estep", fixed_iters=2)
+        run("lidar50k_L5", c5_subsample(), 5, "estep", fixed_iters=2)
     elif what == "c5_50k":
         P = c5_subsample()
         run("lidar50k_L5", P, 5, "estep")

@@ -158,6 +158,53 @@ def registration(target, pi, mu, cov, max_level, lambda_c=0.01, maxiter=20, tol=
 
 
 # --------------------------------------------------------------------------------------
+# Flat-mixture registration (BASELINE configs[3]).  The reference's entry point for it,
+# GMMRegistration::pointCloudRegisterGPU (src/c++/gmm_registration/gmm_reg.cu:54-56), is an empty
+# stub, so there is nothing of the reference's to pin this against: PARITY UNPINNED BY THE REFERENCE.
+# What is restated is the north star's definition -- the flat E-step (gmm_kernels.cu:278-302
+# responsibilities, as oracle/flat_gmm.py::cpp_em_iteration evaluates them) used as point-to-mixture
+# correspondence, feeding the same two solves as the tree registration above.
+# --------------------------------------------------------------------------------------
+def flat_reg_moments(Y, weights, mu, cov):
+    """responsibilities of the (already transformed) target over all J components of a full-covariance
+    mixture -> (S0 [J] = sum_i gamma_ij, S1 [J,3] = sum_i gamma_ij y_i)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    d = Y[:, None, :] - mu[None, :, :]
+    inv = np.linalg.inv(cov)
+    maha = np.einsum("nja,jab,njb->nj", d, inv, d)
+    with np.errstate(divide="ignore"):
+        a = np.log(weights)[None, :] - 0.5 * (3.0 * np.log(2.0 * np.pi) + np.log(np.linalg.det(cov))[None, :] + maha)
+    m = a.max(axis=1, keepdims=True)
+    e = np.exp(a - m)
+    g = e / e.sum(axis=1, keepdims=True)
+    return g.sum(axis=0), g.T @ Y
+
+
+def flat_registration(target, weights, mu, cov, maxiter=20, tol=1.0e-4, solver="procrustes", rot=None, t=None):
+    """the loop of `registration` above with the flat E-step; returns the INVERSE transform (R^T, -R^T t),
+    the last q and the iteration count (same conventions as GMMTree.registration, hgmm_gpu.py:754-768)."""
+    Y = np.asarray(target, dtype=np.float64)
+    weights, mu, cov = (np.asarray(v, dtype=np.float64) for v in (weights, mu, cov))
+    rot = np.identity(3) if rot is None else np.array(rot, dtype=np.float64)
+    t = np.zeros(3) if t is None else np.array(t, dtype=np.float64)
+    q_prev = None
+    it = 0
+    for it in range(1, maxiter + 1):
+        S0, S1 = flat_reg_moments(Y @ rot.T + t, weights, mu, cov)
+        if solver == "twist_lstsq":
+            H, g, c = reg_normal_equations(S0, S1, mu, cov)
+            x = np.linalg.solve(H, g)
+            q = float(c - g @ x)
+            rot, t = twist_mul(x, rot, t)
+        else:
+            rot, t, q = reg_m_step_procrustes(S0, S1, mu, rot, t)
+        if q_prev is not None and abs(q - q_prev) < tol:
+            break
+        q_prev = q
+    return rot.T, -rot.T @ t, q, it
+
+
+# --------------------------------------------------------------------------------------
 # McAdams / Selle / Tamstorf / Teran / Sifakis 3x3 SVD as arranged in common/svd3.h
 # --------------------------------------------------------------------------------------
 _GAMMA = 5.828427124      # svd3.h: 3 + 2*sqrt(2)

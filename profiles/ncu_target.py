@@ -25,12 +25,11 @@ elif what == "reg":
         eng.fit_tree(init, 3, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False, want_outputs=False)
         eng.register_tree(solver="twist_lstsq", maxiter=20, tol=1e-4)
 else:
-    from oracle import synth
-    from hgmm_b200 import hgmm as H
+    from hgmm_b200 import hgmm as H, synth
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
     L = int(sys.argv[3]) if len(sys.argv) > 3 else 4
     P = synth.lidar_sweep(n, seed=2024)
     init = P[H.reference_init_indices(L)]
     eng.set_points(torch.from_numpy(P).cuda())
     for _ in range(2):
-        eng.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=25.0, ll_mode="estep", want_current=False, want_outputs=False)
+        eng.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4.0, ll_mode="estep", want_current=False, want_outputs=False)

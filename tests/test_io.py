@@ -125,6 +125,25 @@ def test_pcd_binary_and_ascii(tmp_path):
         io.read_pcd(s)
 
 
+@pytest.mark.parametrize("header", [
+    "FIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1\n",          # COUNT shorter than FIELDS
+    "FIELDS x y z intensity\nSIZE 4 4 4 -4\nTYPE F F F F\nCOUNT 1 1 1 1\n",       # negative SIZE on a trailing field
+    "FIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 -7\n",       # negative COUNT
+    "FIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 0\n",        # zero COUNT
+    "FIELDS x y z blob\nSIZE 4 4 4 8\nTYPE F F F F\nCOUNT 1 1 1 2000000000\n",    # absurd row size
+])
+def test_pcd_hostile_headers_are_rejected_not_fatal(tmp_path, header):
+    """untrusted headers: a bad COUNT / SIZE must come back as HGMM_ERR_IO, never read out of bounds, never let an
+    exception cross the C ABI"""
+    from hgmm_b200 import io, HgmmError
+    f = tmp_path / "bad.pcd"
+    with open(f, "wb") as fh:
+        fh.write(("VERSION 0.7\n" + header + "WIDTH 4\nHEIGHT 1\nPOINTS 4\nDATA binary\n").encode())
+        fh.write(b"\0" * 256)
+    with pytest.raises(HgmmError):
+        io.read_pcd(f)
+
+
 def test_c_abi_two_pass_protocol(tmp_path):
     """capacity smaller than the file: the count is still reported, only `capacity` points are written"""
     import ctypes as C
