@@ -668,7 +668,9 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
     for (int l = 0; l < L && persist; ++l) {
         const int64_t cnt = level_count_h(l);
         const size_t stride = kAccHdr + (size_t)cnt * kMom;
-        CK(cudaMemsetAsync(ctrl, 0, 8 * sizeof(int), s));
+        // ctrl[7] (abort) is cleared once per build and is sticky across its levels: after a failed wait on a peer the
+        // remaining level kernels return at once instead of each running into the deadline
+        CK(cudaMemsetAsync(ctrl, 0, (l == 0 ? 8 : 7) * sizeof(int), s));
         CK(cudaMemsetAsync(qstate, 0, 4 * sizeof(double), s));
         CK(cudaMemsetAsync(ctx->gbar.p, 0, 4 * sizeof(unsigned), s));
         CK(cudaMemsetAsync(acc, 0, 2 * stride * sizeof(double), s));
@@ -702,6 +704,8 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
         for (int l = 0; l < L; ++l) {
             if (ctx->h_lvl[8 * l + 7])
                 FAIL(HGMM_ERR_NCCL, "tree level kernel: a wait on a peer rank timed out (rank missing, or the ranks' call sequences differ)");
+        }
+        for (int l = 0; l < L; ++l) {
             if (!ctx->h_lvl[8 * l]) FAIL(HGMM_ERR_CUDA, "tree level kernel ended without a verdict");
             if (out_iters) out_iters[l] = ctx->h_lvl[8 * l + 1];
             if (out_q) out_q[l] = ctx->h_dbl[32 + 2 * l + 1];

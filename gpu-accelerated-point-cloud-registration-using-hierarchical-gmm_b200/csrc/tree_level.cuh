@@ -479,53 +479,68 @@ __global__ void __launch_bounds__(kTlThreads, 1) tree_level_kernel(const TreeLev
             accp[0] = 0.0;
             for (int r = 0; r < R; ++r) cell16_put(a.x.ll[r] + (size_t)par * kXchgMaxRanks + me, ql, tag_out);
         }
-        // pass 1: nodes owned elsewhere -- push this rank's ten sums into the owner's window (no waiting in this pass)
-        if (R > 1)
-            for (int j = tid * G + b; j < a.cnt; j += kTlThreads * G) {
+        // pass 1: sums of nodes owned elsewhere -> the owner's window (no waiting in this pass).  One cell per thread, consecutive
+        // threads on consecutive cells: a warp's store is 512 contiguous bytes on the NVLink, not 32 scattered 8-byte writes
+        if (R > 1) {
+            const int total = a.cnt * kMom;
+            for (int idx = b * kTlThreads + tid; idx < total; idx += G * kTlThreads) {
+                const int j = idx / kMom, k = idx - j * kMom;
                 const int owner = (j >> 5) % R;
                 if (owner == me) continue;
-                double* Ag = accp + kAccHdr + (size_t)j * kMom;
-                uint4* dst = a.x.mom[owner] + (size_t)par * a.x.mom_cap + ((size_t)me * owned_cap + (size_t)((j >> 5) / R) * 32 + (j & 31)) * kMom;
-#pragma unroll
-                for (int k = 0; k < kMom; ++k) {
-                    cell16_put(dst + k, __ldcg(Ag + k), tag_out);
-                    Ag[k] = 0.0;
-                }
+                double* Ag = accp + kAccHdr + idx;
+                uint4* dst = a.x.mom[owner] + (size_t)par * a.x.mom_cap + ((size_t)me * owned_cap + (size_t)((j >> 5) / R) * 32 + (j & 31)) * kMom + k;
+                cell16_put(dst, __ldcg(Ag), tag_out);
+                *Ag = 0.0;
             }
-        // pass 2: owned nodes -- add the ranks' contributions in rank order, M-step, publish to every rank
-        for (int j = tid * G + b; j < a.cnt; j += kTlThreads * G) {
-            if (R > 1 && (j >> 5) % R != me) continue;
-            double* Ag = accp + kAccHdr + (size_t)j * kMom;
-            double A[kMom];
-            if (R == 1) {
+        }
+        // pass 2: owned nodes, one warp per 32-node slice (slices are dealt round-robin to the ranks, a rank's slices round-robin to
+        // the CTAs): add the ranks' contributions in rank order, M-step, publish to every rank through a shared-memory
+        // transpose so that the 320 parameter cells of the slice leave as contiguous 256-byte stores
+        {
+            float* pkst = stage + warp * (32 * kPkWords);                 // the fold stage is idle between the barrier and the next E-step
+            const int n_slices = (a.cnt + 31) >> 5;
+            for (int os = warp * G + b; ; os += W * G) {                  // os: index among this rank's slices
+                const int sl = me + R * os;
+                if (sl >= n_slices) break;
+                const int j = sl * 32 + lane;
+                const bool live = j < a.cnt;
+                double A[kMom];
 #pragma unroll
-                for (int k = 0; k < kMom; ++k) A[k] = __ldcg(Ag + k);
-            } else {
-                double own[kMom];
+                for (int k = 0; k < kMom; ++k) A[k] = 0.0;
+                if (live) {
+                    double* Ag = accp + kAccHdr + (size_t)j * kMom;
+                    double own[kMom];
 #pragma unroll
-                for (int k = 0; k < kMom; ++k) { own[k] = __ldcg(Ag + k); A[k] = 0.0; }
-                const uint4* src0 = a.x.mom[me] + (size_t)par * a.x.mom_cap + ((size_t)((j >> 5) / R) * 32 + (j & 31)) * kMom;
-                for (int r = 0; r < R; ++r) {
-                    if (r == me) {
+                    for (int k = 0; k < kMom; ++k) { own[k] = __ldcg(Ag + k); Ag[k] = 0.0; }
+                    const uint4* src0 = a.x.mom[me] + (size_t)par * a.x.mom_cap + ((size_t)os * 32 + lane) * kMom;
+                    for (int r = 0; r < R; ++r) {
+                        if (r == me) {
 #pragma unroll
-                        for (int k = 0; k < kMom; ++k) A[k] += own[k];
-                    } else {
-                        double v[kMom];
-                        if (!cell16_get<kMom>(src0 + (size_t)r * owned_cap * kMom, tag_out, v, a)) { aborted = true; break; }
+                            for (int k = 0; k < kMom; ++k) A[k] += own[k];
+                        } else {
+                            double v[kMom];
+                            if (!cell16_get<kMom>(src0 + (size_t)r * owned_cap * kMom, tag_out, v, a)) { aborted = true; break; }
 #pragma unroll
-                        for (int k = 0; k < kMom; ++k) A[k] += v[k];
+                            for (int k = 0; k < kMom; ++k) A[k] += v[k];
+                        }
                     }
                 }
-            }
-#pragma unroll
-            for (int k = 0; k < kMom; ++k) Ag[k] = 0.0;
-            if (aborted) break;
-            const PackedComp pc = tree_mstep_apply(a.t, a.lb, j, A, a.n_total, a.ld);     // writes t.pi / t.mu / t.cov / t.packed
-            const float* pf = reinterpret_cast<const float*>(&pc);
-            for (int r = 0; r < R; ++r) {
-                unsigned long long* dst = a.x.pk[r] + (size_t)j * kPkWords;
-#pragma unroll
-                for (int w = 0; w < kPkWords; ++w) cell8_put(dst + w, pf[w], tag_out);
+                if (__any_sync(0xffffffffu, aborted)) { aborted = true; break; }
+                __syncwarp();
+                if (live) {
+                    const PackedComp pc = tree_mstep_apply(a.t, a.lb, j, A, a.n_total, a.ld);     // writes t.pi / t.mu / t.cov / t.packed
+                    pkst[lane * kPkWords + 0] = pc.mx; pkst[lane * kPkWords + 1] = pc.my; pkst[lane * kPkWords + 2] = pc.mz;
+                    pkst[lane * kPkWords + 3] = pc.c2; pkst[lane * kPkWords + 4] = pc.axx; pkst[lane * kPkWords + 5] = pc.ayy;
+                    pkst[lane * kPkWords + 6] = pc.azz; pkst[lane * kPkWords + 7] = pc.axy; pkst[lane * kPkWords + 8] = pc.axz;
+                    pkst[lane * kPkWords + 9] = pc.ayz;
+                }
+                __syncwarp();
+                const int ncell = min(32, a.cnt - sl * 32) * kPkWords;
+                for (int r = 0; r < R; ++r) {
+                    unsigned long long* dst = a.x.pk[r] + (size_t)sl * 32 * kPkWords;
+                    for (int c = lane; c < ncell; c += 32) cell8_put(dst + c, pkst[c], tag_out);
+                }
+                __syncwarp();
             }
         }
         TL_STAMP(3);

@@ -1,5 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "registration_steps" 2>&1 | grep -E "v = |passed|failed" | cut -c1-1200) > gpurun_out/r2_dbgA.log
-(HGMM_LIB_PATH=$GRAFT_REPO_ROOT/gpu-accelerated-point-cloud-registration-using-hierarchical-gmm_b200/hgmm_b200/libhgmm_vb.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "registration_steps or registration_loop or flat_registration" 2>&1 | grep -E "v = |passed|failed|FAILED" | cut -c1-1200) > gpurun_out/r2_dbgB.log
-cat gpurun_out/r2_dbgA.log gpurun_out/r2_dbgB.log
+timeout 600 python profiles/dump_tree.py persist 2>&1 | grep -v Warning | tail -5
+HGMM_TREE_LEGACY=1 timeout 600 python profiles/dump_tree.py legacy 2>&1 | grep -v Warning | tail -5
+(timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_parity.py::test_tree_config_size_matches_oracle_golden --deselect tests/test_gpu_parity.py::test_tree_config_size_long_run_stays_within_the_fp32_storage_envelope --deselect tests/test_gpu_parity.py::test_tree_config_size_converged_against_oracle_golden 2>&1 | tail -30) > gpurun_out/r2_all.log
+grep -E "passed|failed|FAILED|Error" gpurun_out/r2_all.log | head

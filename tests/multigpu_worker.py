@@ -28,7 +28,7 @@ def main():
     shard = hd.shuffled_shard(X, rank, world, seed=5)
     eng = hgmm_b200.Engine(local)
     hd.attach_communicator(eng)
-    eng.set_points(shard)
+    eng.set_points(shard)                       # no declared total: the shard sizes are all-reduced
     assert eng.total_points == len(X), (eng.total_points, len(X))
     ok = True
     # ---- flat, both flavours
@@ -53,11 +53,6 @@ def main():
     dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
     replicas_identical = bool((lo_ == hi_).all().item())
-    if p2p_on:
-        eng.p2p_detach()                         # same fits over ncclAllReduce
-        r8n = eng.fit_flat(mu8, cov8, w8, cov_type="full", max_iter=8)
-    else:
-        r8n = r8
     # ---- tree
     L = 3
     init = X[H.reference_init_indices(L)]
@@ -69,6 +64,24 @@ def main():
     T = (X @ R.T + np.array([0.002, -0.001, 0.003])).astype(np.float32)
     eng.reg_set_target(hd.shuffled_shard(T, rank, world, seed=6))
     rot, t, q, it, _ = eng.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+    # ---- flat-mixture registration with a sharded target (model: a J = 100 fit of the sharded source)
+    Jr = 100
+    mur = X[np.random.default_rng(4).choice(len(X), Jr, replace=False)]
+    covr = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (Jr, 1, 1))
+    wr = np.full(Jr, 1 / Jr, np.float32)
+    eng.fit_flat(mur, covr, wr, cov_type="full", max_iter=10, want_outputs=False)
+    frot, ft, fq, fit_, _ = eng.register_flat(solver="procrustes_svd", maxiter=15, tol=1e-9)
+    # ---- a deeper tree at a FIXED iteration count (every level's exchange, 4096 leaves, near-empty nodes)
+    L4 = 4
+    init4 = X[H.reference_init_indices(L4)]
+    t4 = eng.fit_tree(init4, L4, ls=0.0, ld=1e-4, sig2=4e-4, ll_mode="estep", max_iters_per_level=6, want_current=False)
+    # ---- the same flat / tree fits over ncclAllReduce (no peer-memory windows: the multi-kernel tree path)
+    if p2p_on:
+        eng.p2p_detach()
+        r8n = eng.fit_flat(mu8, cov8, w8, cov_type="full", max_iter=8)
+        tren = eng.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False)
+    else:
+        r8n, tren = r8, tre
     if rank == 0:
         ref = hgmm_b200.Engine(local)          # no communicator: the whole cloud on one GPU
         ref.set_points(X)
@@ -78,6 +91,9 @@ def main():
         tse = ref.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False)
         ref.reg_set_target(T)
         rot1, t1, q1, it1, _ = ref.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+        ref.fit_flat(mur, covr, wr, cov_type="full", max_iter=10, want_outputs=False)
+        frot1, ft1, fq1, fit1, _ = ref.register_flat(solver="procrustes_svd", maxiter=15, tol=1e-9)
+        s4 = ref.fit_tree(init4, L4, ls=0.0, ld=1e-4, sig2=4e-4, ll_mode="estep", max_iters_per_level=6, want_current=False)
         s8 = ref.fit_flat(mu8, cov8, w8, cov_type="full", max_iter=8)
         sdt = ref.fit_flat(mu8, np.full((J8, 3), 1e-4, np.float32), w8, cov_type="diag", max_iter=40, tol=1e-3)
         assert replicas_identical, "ranks hold different replicas"
@@ -92,12 +108,16 @@ def main():
             "flat_diag": max(rel_fro(rd["means"], sd["means"]), rel_fro(rd["covs"], sd["covs"]), rel_fro(rd["weights"], sd["weights"])),
             "tree_level": max(rel_fro(tr["pi"], ts["pi"]), rel_fro(tr["mu"], ts["mu"]), rel_fro(tr["cov"], ts["cov"])),
             "tree_estep": max(rel_fro(tre["pi"], tse["pi"]), rel_fro(tre["mu"], tse["mu"]), rel_fro(tre["cov"], tse["cov"])),
+            "tree_estep_nccl": max(rel_fro(tren["pi"], tse["pi"]), rel_fro(tren["mu"], tse["mu"]), rel_fro(tren["cov"], tse["cov"])),
             "reg": max(rel_fro(rot, rot1), float(np.abs(t - t1).max())),
+            "flat_reg": max(rel_fro(frot, frot1), float(np.abs(ft - ft1).max())),
+            "tree_L4_fixed6": max(rel_fro(t4["pi"], s4["pi"]), rel_fro(t4["mu"], s4["mu"]), rel_fro(t4["cov"], s4["cov"])),
         }
         print("MULTIGPU", world, errs, "iters", tr["iters"].tolist(), ts["iters"].tolist(), it, it1, flush=True)
         # BASELINE tolerance; observed 1e-6 .. 8e-5 (fp32 atomics order in the tree E-step)
         ok = all(v < 1e-4 for v in errs.values())
         ok = ok and tr["iters"].tolist() == ts["iters"].tolist() and tre["iters"].tolist() == tse["iters"].tolist() and it == it1
+        ok = ok and fit_ == fit1 and t4["iters"].tolist() == s4["iters"].tolist() == [6] * L4
         ref.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
