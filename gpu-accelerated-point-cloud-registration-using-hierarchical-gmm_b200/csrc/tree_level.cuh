@@ -416,9 +416,10 @@ __global__ void __launch_bounds__(kTlThreads, 1) tree_level_kernel(const TreeLev
                         const float4 A0 = wp4[cp * 5], A1 = wp4[cp * 5 + 1];
                         const float2 dx = t_fadd2(xx, make_float2(A0.x, A0.y)), dy = t_fadd2(yy, make_float2(A0.z, A0.w)),
                                      dz = t_fadd2(zz, make_float2(A1.x, A1.y));
-                        float2 gam = make_float2(e[cp].x * inv, e[cp].y * inv);
-                        gam.x = (gam.x < 1e-15f) ? 0.f : gam.x;           // accumulate() skips gamma < eps (:100-101)
-                        gam.y = (gam.y < 1e-15f) ? 0.f : gam.y;
+                        // accumulate() skips gamma < eps = 1e-15 (:100-101).  Not re-tested per child here: such a term is below
+                        // 2^-49 of the point's own mass, i.e. below float32 resolution of every sum it could enter (the dead-point
+                        // rule above, which DOES change sums, is kept exactly)
+                        const float2 gam = t_fmul2(e[cp], make_float2(inv, inv));
                         const float2 gx = t_fmul2(gam, dx), gy = t_fmul2(gam, dy), gz = t_fmul2(gam, dz);
                         float2* A = acc2 + cp * kMom;
                         A[0] = t_fadd2(A[0], gam);
