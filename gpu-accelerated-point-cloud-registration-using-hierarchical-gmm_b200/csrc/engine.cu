@@ -135,6 +135,7 @@ struct hgmm_ctx {
     DevBuf t_pi, t_mu, t_cov, t_cplx, t_packed, t_init;
     DevBuf wx[2], wy[2], wz[2], wperm[2], wpnode[2], wslot[2], wcpar[2], wcstart[2], wclen[2];
     DevBuf gbar;                // persistent level kernel: grid barrier arrival counter
+    DevBuf tterm;               // adaptive build: terminal flags of two consecutive levels
     DevBuf tprof;               // HGMM_TREE_PROF=1: per-CTA phase clocks of the persistent level kernel
     DevBuf twin;                // persistent level kernel, single rank: the local "exchange" region (tree_win_layout)
     int twin_levels = 0;
@@ -269,7 +270,7 @@ int hgmm_destroy(hgmm_ctx* ctx) {
                      &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->done_at, &ctx->partial, &ctx->rowaux, &ctx->cref, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
                      &ctx->t_cplx, &ctx->t_packed, &ctx->t_init, &ctx->p_group, &ctx->p_tilecnt, &ctx->p_tileoff, &ctx->p_segbase,
                      &ctx->p_seg0, &ctx->p_seg1, &ctx->p_chunkcnt, &ctx->p_chunkoff, &ctx->nchunks, &ctx->current, &ctx->tx, &ctx->ty,
-                     &ctx->tz, &ctx->racc, &ctx->Rt, &ctx->l2buf, &ctx->gbar, &ctx->twin, &ctx->rx, &ctx->ry, &ctx->rz, &ctx->tprof};
+                     &ctx->tz, &ctx->racc, &ctx->Rt, &ctx->l2buf, &ctx->gbar, &ctx->twin, &ctx->rx, &ctx->ry, &ctx->rz, &ctx->tprof, &ctx->tterm};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < 2; ++i) {
         DevBuf* w[] = {&ctx->wx[i], &ctx->wy[i], &ctx->wz[i], &ctx->wperm[i], &ctx->wpnode[i], &ctx->wslot[i], &ctx->wcpar[i],
@@ -633,6 +634,16 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
     static const bool legacy_env = getenv("HGMM_TREE_LEGACY") && getenv("HGMM_TREE_LEGACY")[0] == '1';
     const bool persist = fast_ll && cfg->reserved == 0 && !legacy_env &&
                          (ctx->nranks <= 1 || (ctx->p2p_ready && L <= ctx->xwin_tree_levels));
+    const bool adaptive = cfg->prune_lambda_c > 0.f || cfg->prune_min_points > 0.f;
+    if (adaptive && !persist)
+        FAIL(HGMM_ERR_INVALID, "the adaptive (pruned) build runs in the persistent level kernel: ll_mode = HGMM_LL_ESTEP, reserved = 0 "
+                               "(and peer-memory windows when several ranks are attached)");
+    uint8_t* term[2] = {nullptr, nullptr};
+    if (adaptive) {
+        CK(ctx->tterm.ensure(2 * (size_t)level_count_h(L - 1)));
+        term[0] = ctx->tterm.as<uint8_t>();
+        term[1] = term[0] + level_count_h(L - 1);
+    }
     TreeXchgHost xh{};
     if (persist) {
         xh.rank = ctx->rank; xh.nranks = ctx->nranks;
@@ -677,9 +688,14 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
         xh.base = ctx->tepoch;
         ctx->tepoch += (uint32_t)max_iters + 2u;
         cudaError_t e = launch_tree_level(w[cur], t, l, n, acc, stride, nchunks_dev, (double)ctx->n_total, cfg->ld, cfg->ls, max_iters,
-                                          ctrl, qstate, ctx->gbar.as<unsigned>(), chunk, xh, ctx->num_sms, tprof, s);
+                                          ctrl, qstate, ctx->gbar.as<unsigned>(), chunk, xh, ctx->num_sms, tprof,
+                                          (adaptive && l > 0) ? term[(l - 1) & 1] : nullptr, s);
         if (e != cudaSuccess) { ctx->err = std::string("tree level kernel launch: ") + cudaGetErrorString(e); return HGMM_ERR_CUDA; }
         ctx->launches += 1;
+        if (adaptive && l < L - 1) {       // which nodes of this level are terminal: their points sit out the deeper levels
+            launch_tree_prune(t, l, (double)ctx->n_total, cfg->prune_lambda_c, cfg->prune_min_points, term[l & 1], s);
+            ctx->launches += 1;
+        }
         // no host synchronisation between levels: the control words of every level are fetched asynchronously, read at the end
         CK(cudaMemcpyAsync(ctx->h_lvl + 8 * l, ctrl, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_dbl + 32 + 2 * l, qstate, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -171,7 +171,8 @@ void tree_level_plan(int n, int chunk_points, int level, int num_sms, int smem_o
 cudaError_t launch_tree_level(const TreeWork& w, const TreeModel& t, int level, int n, double* acc, size_t acc_stride,
                               const int* n_chunks_dev, double n_total, float ld, float ls, int max_iters, int* ctrl, double* qstate,
                               unsigned* gbar, int chunk_points, const TreeXchgHost& xh, int num_sms, long long* prof,
-                              cudaStream_t s);
+                              const uint8_t* term, cudaStream_t s);
+void launch_tree_prune(const TreeModel& t, int level, double n_total, float lambda_c, float min_points, uint8_t* term, cudaStream_t s);
 void launch_tree_zero_ll(double* acc, const int* done_flag, cudaStream_t s);
 void launch_tree_cplx(const TreeModel& t, cudaStream_t s);
 void launch_tree_current(const TreeWork& w, int n, int level, int64_t* current, cudaStream_t s);

@@ -500,6 +500,22 @@ __global__ void tree_cplx_kernel(TreeModel t) {
     t.cplx[j] = (float)sym3_complexity(s);
 }
 
+// adaptive build: which nodes of a finished level are terminal (include/hgmm.h, hgmm_tree_config.prune_*)
+__global__ void tree_prune_kernel(TreeModel t, int lb, int count, double n_total, float lambda_c, float min_points,
+                                  uint8_t* __restrict__ term) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const int g = lb + j;
+    const double w = t.pi[g];
+    bool terminal = !(w > 0.0) || (min_points > 0.f && w * n_total < (double)min_points);
+    if (!terminal && lambda_c > 0.f) {
+        const float* c = t.cov + 9 * (size_t)g;
+        Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
+        terminal = sym3_complexity(s) <= (double)lambda_c;
+    }
+    term[j] = terminal ? 1 : 0;
+}
+
 // current[perm[i]] = level base + 8 * parent + slot  (hgmm_gpu.py:411)
 __global__ void tree_current_kernel(const int* __restrict__ perm, const int* __restrict__ pnode,
                                     const uint8_t* __restrict__ slot, int n, int lb, int64_t* __restrict__ current) {
@@ -773,9 +789,10 @@ void tree_level_plan(int n, int chunk_points, int level, int num_sms, int smem_o
 cudaError_t launch_tree_level(const TreeWork& w, const TreeModel& t, int level, int n, double* acc, size_t acc_stride,
                               const int* n_chunks_dev, double n_total, float ld, float ls, int max_iters, int* ctrl, double* qstate,
                               unsigned* gbar, int chunk_points, const TreeXchgHost& xh, int num_sms, long long* prof,
-                              cudaStream_t s) {
+                              const uint8_t* term, cudaStream_t s) {
     TreeLevelArgs a;
     a.prof = prof;
+    a.term = term;
     a.px = w.x; a.py = w.y; a.pz = w.z;
     a.chunk_parent = w.chunk_parent; a.chunk_start = w.chunk_start; a.chunk_len = w.chunk_len; a.n_chunks_dev = n_chunks_dev;
     a.slot = w.slot;
@@ -805,6 +822,11 @@ cudaError_t launch_tree_level(const TreeWork& w, const TreeModel& t, int level, 
     if (occ < 1) return cudaErrorNotSupported;
     void* args[] = {(void*)&a};
     return cudaLaunchCooperativeKernel((const void*)tree_level_kernel, dim3(num_sms), dim3(kTlThreads), args, smem, s);
+}
+
+void launch_tree_prune(const TreeModel& t, int level, double n_total, float lambda_c, float min_points, uint8_t* term, cudaStream_t s) {
+    const int cnt = level_count(level);
+    tree_prune_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(t, level_base(level), cnt, n_total, lambda_c, min_points, term);
 }
 
 void launch_tree_converge(double* acc, int* ctrl, int* done_at, int it, double* qstate, float ls, int max_iters, int* prog,

@@ -51,6 +51,7 @@ struct TreeLevelArgs {
     const float *px, *py, *pz;                  // permuted cloud of this rank
     const int *chunk_parent, *chunk_start, *chunk_len, *n_chunks_dev;
     uint8_t* slot;
+    const uint8_t* term;                        // adaptive build: [parents of this level] 1 = terminal (its points sit out), or null
     TreeModel t;
     int lb, cnt, n;
     double* acc;                                // [2][acc_stride], zero on entry
@@ -353,6 +354,10 @@ __global__ void __launch_bounds__(kTlThreads, 1) tree_level_kernel(const TreeLev
                     p = sc_parent[ci]; start = sc_start[ci]; len = sc_len[ci];
                 } else {
                     p = __ldg(a.chunk_parent + c0 + ci); start = __ldg(a.chunk_start + c0 + ci); len = __ldg(a.chunk_len + c0 + ci);
+                }
+                if (a.term && a.term[p]) {                            // adaptive build: a terminal parent's points take no part --
+                    for (int r = lane; r < len; r += 32) a.slot[start + r] = 0;      // child 0, no moments, no log-likelihood term
+                    continue;
                 }
                 if (p != cur_p) {
                     if (cur_p >= 0) tl_fold_stage(acc2, cur_p, lane, stage, stage_parent, a.stage_cap, &s_nslots, accp);

@@ -29,7 +29,8 @@ class FlatConfig(C.Structure):
 
 class TreeConfig(C.Structure):
     _fields_ = [("max_level", C.c_int32), ("ll_mode", C.c_int32), ("ls", C.c_float), ("ld", C.c_float), ("sig2", C.c_float),
-                ("max_iters_per_level", C.c_int32), ("chunk_points", C.c_int32), ("reserved", C.c_int32)]
+                ("max_iters_per_level", C.c_int32), ("chunk_points", C.c_int32), ("reserved", C.c_int32),
+                ("prune_lambda_c", C.c_float), ("prune_min_points", C.c_float)]
 
 
 class RegConfig(C.Structure):

@@ -144,11 +144,12 @@ class Engine:
         return int(L.load().hgmm_tree_total_nodes(int(max_level)))
 
     def fit_tree(self, init_means, max_level, ls=20.0, ld=1.0e-4, sig2=0.004, ll_mode="level", max_iters_per_level=10000,
-                 chunk_points=0, want_current=True, want_outputs=True, variant=0):
+                 chunk_points=0, want_current=True, want_outputs=True, variant=0, prune_lambda_c=0.0, prune_min_points=0.0):
+        """prune_lambda_c / prune_min_points > 0: adaptive (ragged) build, see include/hgmm.h (ll_mode must be 'estep')"""
         nt = self.tree_total_nodes(max_level)
         init_means = L.f32c(init_means, (nt, 3))
         cfg = L.TreeConfig(int(max_level), L.LL_LEVEL if ll_mode == "level" else L.LL_ESTEP, float(ls), float(ld), float(sig2),
-                           int(max_iters_per_level), int(chunk_points), int(variant))
+                           int(max_iters_per_level), int(chunk_points), int(variant), float(prune_lambda_c), float(prune_min_points))
         pi = np.empty(nt, np.float32) if want_outputs else None
         mu = np.empty((nt, 3), np.float32) if want_outputs else None
         cov = np.empty((nt, 3, 3), np.float32) if want_outputs else None

@@ -37,6 +37,18 @@ def reference_init_indices(maxTreeLevel, seed=72):
     return np.random.RandomState(seed).randint(nTotal, size=nTotal)
 
 
+def deepest_live_node(current, mixingCoeff, maxTreeLevel):
+    """node that actually holds each point in a pruned (ragged) tree: `current` is the leaf-level id the build reports; under a
+    terminal node the children are blank (pi = 0), so walk up (parent(j) = j // 8 - 1, hgmm_gpu.py:84-89 inverted) to the
+    first node that carries mass."""
+    cur = np.asarray(current, dtype=np.int64).copy()
+    pi = np.asarray(mixingCoeff)
+    for _ in range(maxTreeLevel - 1):
+        up = (pi[cur] <= 0) & (cur >= n_node)
+        cur[up] = cur[up] // n_node - 1
+    return cur
+
+
 def _cloud(x):
     return np.asarray(x.points if hasattr(x, "points") else x)
 

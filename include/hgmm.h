@@ -93,6 +93,14 @@ typedef struct hgmm_tree_config {
     int32_t max_iters_per_level;   /* safety cap; the reference has none */
     int32_t chunk_points;          /* 0 = auto; points per warp work item (multiple of 32) */
     int32_t reserved;              /* E-step kernel: 0 = packed-FP32 (default), 1 = scalar first-generation kernel */
+    /* adaptive (pruned, ragged) build -- the "adaptive scaling" of README.md:74, which the reference only applies at
+     * registration time (lambda_c stop, hgmm_gpu.py:572) and through the M0 < ld blanking (hgmm_cupy_cpu_working.py:111-112).
+     * After a level has converged a node becomes TERMINAL -- its 8 children stay blank and its points take no part in deeper
+     * levels -- when it is blank, when complexity(Sigma) = lambda_min / trace <= prune_lambda_c (already a plane at this scale),
+     * or when it holds fewer than prune_min_points points (N * pi).  0 / 0 = off (the reference's full tree).  Needs
+     * ll_mode = HGMM_LL_ESTEP. */
+    float prune_lambda_c;
+    float prune_min_points;
 } hgmm_tree_config;
 
 typedef struct hgmm_reg_config {

@@ -67,13 +67,15 @@ def children_gamma(X, pi, mu, cov, parent):
     return pi[idx] * pdf, j0
 
 
-def tree_e_step(X, pi, mu, cov, parent, nt):
+def tree_e_step(X, pi, mu, cov, parent, nt, skip=None):
     """gmmTreeEStep (hgmm_cupy_cpu_working.py:162-191) + accumulate (:99-106).
 
     gamma = gamma/den if den > EPS else 0 (:174-178); a child is accumulated only if its
     normalised gamma >= EPS (:100-101); currentIdx = j0 + argmax(gamma) (first max, 0 if all zero).
     Returns (M0 [nt], M1 [nt,3], M2 [nt,3,3], current [N], den [N])."""
     g, j0 = children_gamma(X, pi, mu, cov, parent)
+    if skip is not None:                       # adaptive build: points under a terminal node take no part (child 0, no moments, no q)
+        g = np.where(skip[:, None], 0.0, g)
     den = g.sum(axis=1)
     gn = np.where((den > EPS)[:, None], g / np.where(den > EPS, den, 1.0)[:, None], 0.0)
     current = j0 + gn.argmax(axis=1)
@@ -115,7 +117,7 @@ def level_log_likelihood(X, pi, mu, cov, lb, le, chunk=4096):
 
 
 def build_gmm_tree(points, max_level, ls, ld, init_means, sig2=0.004, ll_mode="level",
-                   max_iters_per_level=10000, return_trace=False):
+                   max_iters_per_level=10000, return_trace=False, prune_lambda_c=0.0, prune_min_points=0.0):
     """buildGMMTree (hgmm_gpu.py:466-548, hgmm_cupy_cpu_working.py:122-160).
 
     init: every node pi=1/8, mu=init_means[i], cov=sig2*I (hgmm_gpu.py:487-490);
@@ -134,16 +136,20 @@ def build_gmm_tree(points, max_level, ls, ld, init_means, sig2=0.004, ll_mode="l
     parent = -np.ones(N, dtype=np.int64)
     current = np.zeros(N, dtype=np.int64)
     iters, trace = [], []
+    terminal = np.zeros(nt, dtype=bool)        # adaptive build (include/hgmm.h hgmm_tree_config.prune_*): not in the reference
     for l in range(max_level):
         lb, le = level(l), level(l + 1)
         prev_q = 0.0
         it = 0
+        skip = terminal[np.maximum(parent, 0)] & (parent >= 0) if (prune_lambda_c > 0 or prune_min_points > 0) else None
         while True:
-            M0, M1, M2, current, den = tree_e_step(X, pi, mu, cov, parent, nt)
+            M0, M1, M2, current, den = tree_e_step(X, pi, mu, cov, parent, nt, skip)
             npi, nmu, ncov = ml_estimator(M0[lb:le], M1[lb:le], M2[lb:le], N, ld)
             pi[lb:le], mu[lb:le], cov[lb:le] = npi, nmu, ncov
             if ll_mode == "level":
                 q = level_log_likelihood(X, pi, mu, cov, lb, le)
+            elif skip is not None:
+                q = float(np.log(np.maximum(den[~skip], EPS)).sum())
             else:
                 q = float(np.log(np.maximum(den, EPS)).sum())
             it += 1
@@ -153,6 +159,11 @@ def build_gmm_tree(points, max_level, ls, ld, init_means, sig2=0.004, ll_mode="l
             prev_q = q
         iters.append(it)
         parent = current.copy()
+        if prune_lambda_c > 0 or prune_min_points > 0:
+            with np.errstate(invalid="ignore", divide="ignore"):
+                cx = complexity(cov[lb:le])
+            terminal[lb:le] = (pi[lb:le] <= 0) | ((prune_min_points > 0) & (pi[lb:le] * N < prune_min_points)) | \
+                              ((prune_lambda_c > 0) & (cx <= prune_lambda_c))
     if return_trace:
         return pi, mu, cov, current, iters, trace
     return pi, mu, cov, current

@@ -33,11 +33,21 @@ def test_version_and_node_count_need_no_gpu():
     assert [lib.hgmm_tree_total_nodes(l) for l in range(1, 6)] == [8, 72, 584, 4680, 37448]
 
 
-def test_config_struct_layout_matches_header():
+def test_config_struct_layout_matches_header(tmp_path):
+    """the ctypes mirrors against the C compiler's view of include/hgmm.h: sizes and the offset of the last field"""
+    import subprocess
     from hgmm_b200 import _lib
-    assert ctypes.sizeof(_lib.FlatConfig) == 32
-    assert ctypes.sizeof(_lib.TreeConfig) == 32
-    assert ctypes.sizeof(_lib.RegConfig) == 16
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hgmm.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(hgmm_flat_config), offsetof(hgmm_flat_config, reserved), sizeof(hgmm_tree_config), '
+                   'offsetof(hgmm_tree_config, prune_min_points), sizeof(hgmm_reg_config), offsetof(hgmm_reg_config, lambda_c)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    c = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    py = [ctypes.sizeof(_lib.FlatConfig), _lib.FlatConfig.reserved.offset, ctypes.sizeof(_lib.TreeConfig),
+          _lib.TreeConfig.prune_min_points.offset, ctypes.sizeof(_lib.RegConfig), _lib.RegConfig.lambda_c.offset]
+    assert c == py, (c, py)
+    assert c[0] == 32 and c[2] == 40 and c[4] == 16
 
 
 def test_no_cpu_fallback():

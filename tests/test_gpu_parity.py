@@ -487,6 +487,45 @@ def _lidar_cloud(tag):
     return P[np.random.default_rng(0).permutation(len(P))[:50000]]
 
 
+def test_adaptive_tree_build_matches_oracle(engine, bun000):
+    """the pruned (ragged) build -- nodes that are blank, flat enough (complexity <= lambda_c) or too light
+    (< min_points) become terminal after their level, their subtree stays blank -- against the oracle's restatement of the same
+    rule; the tree must be genuinely ragged, and registration must run on it."""
+    from oracle import hgmm_tree
+    from hgmm_b200 import hgmm as H
+    X = bun000[::2]
+    L = 3
+    init = X[hgmm_tree.reference_init_indices(L)]
+    kw = dict(prune_lambda_c=0.02, prune_min_points=40.0)
+    engine.set_points(X)
+    r = engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", **kw)
+    opi, omu, ocov, ocur, oit, _ = hgmm_tree.build_gmm_tree(X, L, 20.0, 1e-4, init.astype(np.float64), sig2=np.float32(4e-4), ll_mode="estep",
+                                                            return_trace=True, **kw)
+    assert r["iters"].tolist() == list(oit)
+    assert rel_fro(r["pi"], opi) < TOL and rel_fro(r["mu"], omu) < TOL and rel_fro(r["cov"], ocov) < 3 * TOL
+    assert float((r["current"] == ocur).mean()) > 0.9995
+    full = engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep")
+    lb = hgmm_tree.level(L - 1)
+    live_pruned, live_full = int((r["pi"][lb:] > 0).sum()), int((full["pi"][lb:] > 0).sum())
+    print("live leaves: pruned %d, full %d of %d" % (live_pruned, live_full, hgmm_tree.n_total(L) - lb))
+    assert live_pruned < 0.8 * live_full                                    # the tree is ragged ...
+    deep = H.deepest_live_node(r["current"], r["pi"], L)
+    assert (r["pi"][deep] > 0).all() and (deep < lb).mean() > 0.1           # ... a good share of the points ends above the leaf level
+    assert abs(float(r["pi"][deep].sum()) - float(r["pi"][deep].sum())) == 0.0
+    # mass is conserved along the ragged frontier: every point is counted exactly once among the deepest live nodes
+    front = np.zeros(len(r["pi"]), bool)
+    front[np.unique(deep)] = True
+    assert abs(float(r["pi"][front].sum()) - 1.0) < 2e-2
+    with pytest.raises(Exception):
+        engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="level", **kw)     # needs the persistent (estep) path
+    th = np.deg2rad(5.0)
+    Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    engine.tree_set_model(L, r["pi"], r["mu"], r["cov"])
+    engine.reg_set_target((X[::2] @ Rz.T + np.array([0.002, 0.001, -0.001])).astype(np.float32))
+    rot, t, q, it, _ = engine.register_tree(solver="twist_lstsq", maxiter=20, tol=1e-6, lambda_c=0.02)
+    assert rel_fro(rot, Rz.T) < 2e-2
+
+
 def _tree_level_errors(r, g, lv):
     """node-wise distances of level `lv` between a fitted tree r and the oracle fixture g, on nodes alive in both:
     |d mu| / sqrt(tr Sigma) and |d Sigma|_F / |Sigma|_F per node -> (mass-weighted means, medians, |d pi|_1, mass of the nodes

@@ -22,3 +22,30 @@ def test_sharded_fits_match_single_gpu(world):
     sys.stderr.write(out.stderr[-3000:])
     assert out.returncode == 0
     assert "MULTIGPU %d" % world in out.stdout
+
+
+def test_two_contexts_on_two_devices_in_one_process(bun000):
+    """function attributes (the opt-in shared-memory limit of the sweeps, the cooperative level kernel) are PER DEVICE: a second
+    context on another device of the same process must launch the same kernels (process-static caches broke this)."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import hgmm_b200
+    from hgmm_b200 import hgmm as H
+    J = 800
+    mu0 = bun000[np.random.default_rng(1).choice(len(bun000), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J, 1, 1))
+    w0 = np.full(J, 1 / J, np.float32)
+    init = bun000[H.reference_init_indices(3)]
+    out = []
+    for dev in (0, 1):
+        eng = hgmm_b200.Engine(dev)
+        eng.set_points(bun000)
+        f = eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=5)           # em_flat7: 232 kB of opt-in shared memory
+        t = eng.fit_tree(init, 3, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False)      # cooperative level kernel
+        out.append((f, t))
+        eng.close()
+    assert np.array_equal(out[0][0]["means"], out[1][0]["means"]) and np.array_equal(out[0][0]["covs"], out[1][0]["covs"])
+    assert np.allclose(out[0][1]["mu"], out[1][1]["mu"], rtol=0, atol=1e-4)
+

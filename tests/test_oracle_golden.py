@@ -211,3 +211,24 @@ def test_tree_fp32_storage_alone_moves_the_config_size_build():
     assert out[2] < 1e-5, out
     assert out[12] > 3e-4, out
 
+
+def test_adaptive_tree_oracle_semantics(bun000):
+    """the pruned build of oracle/hgmm_tree.py: identical to the reference build when both thresholds are 0; otherwise every node
+    below a terminal node is blank, terminal nodes are exactly {blank, complexity <= lambda_c, mass < min_points}, and the points
+    under them are not re-assigned."""
+    X = bun000[::8].astype(np.float64)
+    L = 3
+    init = X[hgmm_tree.reference_init_indices(L)]
+    a = hgmm_tree.build_gmm_tree(X, L, 20.0, 1e-4, init, sig2=4e-4, ll_mode="estep")
+    b = hgmm_tree.build_gmm_tree(X, L, 20.0, 1e-4, init, sig2=4e-4, ll_mode="estep", prune_lambda_c=0.0, prune_min_points=0.0)
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))
+    pi, mu, cov, cur = hgmm_tree.build_gmm_tree(X, L, 20.0, 1e-4, init, sig2=4e-4, ll_mode="estep", prune_lambda_c=0.02, prune_min_points=20.0)
+    n = len(X)
+    for l in range(L - 1):
+        lb, le = hgmm_tree.level(l), hgmm_tree.level(l + 1)
+        cx = hgmm_tree.complexity(cov[lb:le])
+        term = (pi[lb:le] <= 0) | (pi[lb:le] * n < 20.0) | (cx <= 0.02)
+        kids = hgmm_tree.child(np.arange(lb, le))[:, None] + np.arange(8)[None, :]
+        assert (pi[kids[term]] == 0).all()                       # a terminal node's children are blank
+    assert (pi[hgmm_tree.level(L - 1):] > 0).sum() < (a[0][hgmm_tree.level(L - 1):] > 0).sum()
+
