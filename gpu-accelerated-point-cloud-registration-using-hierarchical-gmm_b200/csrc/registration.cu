@@ -211,6 +211,116 @@ __global__ void __launch_bounds__(256) reg_estep2_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// E-step, third generation (default).  What the ncu capture of reg_estep_kernel shows (profiles/r01_reg_estep_ncu_full.txt):
+// 1830 warp instructions per 32 points at ~24 stall cycles each, most of them in the fold of the two top levels (every warp
+// scans all 256 parked entries nine times in fp64) and at its barrier; only 8.5 warps per SM exist for a 40k-point cloud.
+// Here the descent only RECORDS (node, gamma) per level in registers; the accumulation is a second, warp-cooperative phase:
+// per level the warp walks its DISTINCT nodes (range scans are spatially coherent: 1-3 per warp), reduces the members'
+// (gamma, gamma x [, gamma x x^T]) with a masked fp64 butterfly and the leader lane adds the result once -- to a small
+// shared-memory table for the 72 nodes of the two top levels (flushed once per CTA), to L2 for deeper ones.  No fold pass,
+// no barrier before the end, 128-thread CTAs (several per SM, one wave).  Semantics are those of reg_estep_kernel /
+// gmmTreeRegESTep (hgmm_gpu.py:550-577): first-maximum arg-max, gamma = 0 when the eight densities sum below 1e-15, stop
+// BEFORE accumulating at a node whose complexity is <= lambda_c, skip gamma < 1e-15.
+// ------------------------------------------------------------------------------------------
+constexpr int kRegMaxL = 6;
+template <int NM>
+__device__ __forceinline__ void reg_accumulate_level(int key, float gam, float x, float y, float z, int lane, double (*s_acc)[kRegMom],
+                                                     double* __restrict__ racc) {
+    unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
+    while (todo) {                                              // warp-uniform: one round per distinct node of the warp
+        const int leader = __ffs(todo) - 1;
+        const int k = __shfl_sync(0xffffffffu, key, leader);
+        const bool mine = key == k;
+        const double g = mine ? (double)gam : 0.0, X = x, Y = y, Z = z;
+        double v[NM];
+        v[0] = g; v[1] = g * X; v[2] = g * Y; v[3] = g * Z;
+        if (NM > 4) { v[4] = g * X * X; v[5] = g * X * Y; v[6] = g * X * Z; v[7] = g * Y * Y; v[8] = g * Y * Z; v[9] = g * Z * Z; }
+#pragma unroll
+        for (int i = 0; i < NM; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        }
+        if (lane == leader) {
+            double* A = k < kTopNodes ? &s_acc[k][0] : racc + (size_t)k * kRegMom;
+#pragma unroll
+            for (int i = 0; i < NM; ++i) atomicAdd(A + i, v[i]);
+        }
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+
+__global__ void __launch_bounds__(128) reg_estep3_kernel(const float* __restrict__ tx, const float* __restrict__ ty,
+                                                         const float* __restrict__ tz, int n, const double* __restrict__ Rt,
+                                                         const PackedComp* __restrict__ packed, const float* __restrict__ cplx,
+                                                         int L, float lambda_c, double* __restrict__ racc, int want_m2,
+                                                         const int* __restrict__ ctrl) {
+    // programmatic dependent launch: the grid is scheduled while the previous solve drains; everything that kernel wrote
+    // (the transform, the stop flag, the zeroed moments) is read after the wait
+    __shared__ double s_acc[kTopNodes][kRegMom];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int k = tid; k < kTopNodes * kRegMom; k += blockDim.x) (&s_acc[0][0])[k] = 0.0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (__ldcg(ctrl)) return;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + tid;
+    float x = 0.f, y = 0.f, z = 0.f;
+    int node[kRegMaxL];
+    float gam[kRegMaxL];
+#pragma unroll
+    for (int l = 0; l < kRegMaxL; ++l) { node[l] = -1; gam[l] = 0.f; }
+    if (i < n) {
+        const double a = tx[i], b = ty[i], c = tz[i];           // t_target = target R^T + t  (hgmm_gpu.py:757,613-614)
+        x = (float)(__ldcg(Rt + 0) * a + __ldcg(Rt + 1) * b + __ldcg(Rt + 2) * c + __ldcg(Rt + 9));
+        y = (float)(__ldcg(Rt + 3) * a + __ldcg(Rt + 4) * b + __ldcg(Rt + 5) * c + __ldcg(Rt + 10));
+        z = (float)(__ldcg(Rt + 6) * a + __ldcg(Rt + 7) * b + __ldcg(Rt + 8) * c + __ldcg(Rt + 11));
+        int j0 = 0;                                             // child(-1) = 0
+#pragma unroll
+        for (int l = 0; l < kRegMaxL; ++l) {
+            if (l >= L) break;
+            const float4* c4 = reinterpret_cast<const float4*>(packed + j0);
+            float q[8];
+            float m = kNegBig;
+            int best = 0;
+#pragma unroll
+            float cx_best = 0.f, cx0 = 0.f;                     // complexity rides in PackedComp::pad0 (tree_cplx_kernel): no
+            for (int k = 0; k < 8; ++k) {                       // second, dependent load per level
+                const float4 p0 = __ldg(c4 + 3 * k), p1 = __ldg(c4 + 3 * k + 1);
+                const float4 p2 = __ldg(c4 + 3 * k + 2);
+                float dx, dy, dz;
+                q[k] = quad_q2(p0, p1, make_float2(p2.x, p2.y), x, y, z, dx, dy, dz);
+                if (k == 0) cx0 = p2.z;
+                if (q[k] > m) { m = q[k]; best = k; cx_best = p2.z; }
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += ex2f(q[k] - m);
+            const float lse2 = m + lg2f(s);
+            const bool alive = lse2 > kLog2Eps15;               // den > eps else gamma = zeros (:563-567)
+            const int sid = j0 + (alive ? best : 0);
+            if ((alive ? cx_best : cx0) <= lambda_c) break;     // :572-573, before accumulating
+            const float g = alive ? 1.0f / s : 0.f;             // gamma of the arg-max child
+            if (g >= 1e-15f) {                                  // accumulate() guard (:457-459)
+                node[l] = sid;
+                gam[l] = g;
+            }
+            j0 = (sid + 1) * 8;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < kRegMaxL; ++l) {
+        if (l >= L) break;                                      // L is warp-uniform: every lane runs the same rounds
+        if (want_m2) reg_accumulate_level<kRegMom>(node[l], gam[l], x, y, z, lane, s_acc, racc);
+        else reg_accumulate_level<4>(node[l], gam[l], x, y, z, lane, s_acc, racc);
+    }
+    __syncthreads();
+    for (int k = tid; k < kTopNodes * kRegMom; k += blockDim.x) {
+        const double v = (&s_acc[0][0])[k];
+        if (v != 0.0) atomicAdd(racc + k, v);                   // racc is [node][kRegMom]: same flat index
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // M-step solves.  One CTA; per-thread partial sums over nodes, fixed-order tree reduction.
 // ------------------------------------------------------------------------------------------
 constexpr int kSys = 28;        // H (21 upper-triangular) + g (6) + c (1)
@@ -245,8 +355,11 @@ __device__ void rodrigues(const double* w, double* R) {      // twist_trans (hgm
         R[1] = R[2] = R[3] = R[5] = R[6] = R[7] = 0.0;
         return;
     }
-    const double nx = w[0] / th, ny = w[1] / th, nz = w[2] / th;
-    const double c = cos(th), s = sin(th), oc = 1.0 - c;
+    const double ith = 1.0 / th;
+    const double nx = w[0] * ith, ny = w[1] * ith, nz = w[2] * ith;
+    double s, c;
+    sincos(th, &s, &c);
+    const double oc = 1.0 - c;
     R[0] = c + oc * nx * nx;      R[1] = oc * nx * ny - s * nz; R[2] = oc * nx * nz + s * ny;
     R[3] = oc * ny * nx + s * nz; R[4] = c + oc * ny * ny;      R[5] = oc * ny * nz - s * nx;
     R[6] = oc * nz * nx - s * ny; R[7] = oc * nz * ny + s * nx; R[8] = c + oc * nz * nz;
@@ -263,29 +376,34 @@ __device__ void compose(const double* dR, const double* dt, double* Rt) {
     for (int k = 0; k < 3; ++k) Rt[9 + k] = tn[k];
 }
 
-// in-place Cholesky solve of the 6x6 SPD system; returns false when not positive definite
+// in-place Cholesky solve of the 6x6 SPD system; returns false when not positive definite.
+// The solve runs on ONE thread between two kernels of every registration iteration, i.e. on the iteration's critical path: the
+// 6 square roots and 27 divisions of the textbook form (each a ~30-instruction fp64 sequence) are replaced by 6 reciprocal square
+// roots (rsqrt: MUFU.RSQ64H + Newton steps, 1 ulp) and multiplications.
 __device__ bool chol6_solve(double* H /*[36]*/, double* g /*[6] in, x out*/) {
+    double invd[6];
     for (int j = 0; j < 6; ++j) {
         double d = H[7 * j];
         for (int k = 0; k < j; ++k) d -= H[6 * j + k] * H[6 * j + k];
         if (!(d > 0.0)) return false;
-        d = sqrt(d);
-        H[7 * j] = d;
+        const double r = rsqrt(d);
+        invd[j] = r;
+        H[7 * j] = d * r;
         for (int i = j + 1; i < 6; ++i) {
             double v = H[6 * i + j];
             for (int k = 0; k < j; ++k) v -= H[6 * i + k] * H[6 * j + k];
-            H[6 * i + j] = v / d;
+            H[6 * i + j] = v * r;
         }
     }
     for (int i = 0; i < 6; ++i) {
         double v = g[i];
         for (int k = 0; k < i; ++k) v -= H[6 * i + k] * g[k];
-        g[i] = v / H[7 * i];
+        g[i] = v * invd[i];
     }
     for (int i = 5; i >= 0; --i) {
         double v = g[i];
         for (int k = i + 1; k < 6; ++k) v -= H[6 * k + i] * g[k];
-        g[i] = v / H[7 * i];
+        g[i] = v * invd[i];
     }
     return true;
 }
@@ -467,6 +585,8 @@ __device__ __forceinline__ void procrustes_finish(const double* v, double* Rt, d
 __global__ void __launch_bounds__(512) reg_solve_kernel(TreeModel t, double* __restrict__ racc, int zero_after, int solver,
                                                         double* __restrict__ Rt, double* __restrict__ q_hist,
                                                         double* __restrict__ qstate, int* __restrict__ ctrl, float tol) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL-chained with the E-step (all of its atomics have landed)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (ctrl[0]) return;
     __shared__ double sm[16 * kSys];
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -637,7 +757,22 @@ __global__ void fill_vbo_kernel(const float* __restrict__ x, const float* __rest
 cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, int n, const double* Rt, const TreeModel& t,
                              float lambda_c, double* racc, int want_m2, const int* ctrl, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    static const bool v2 = getenv("HGMM_REG_ESTEP2") && getenv("HGMM_REG_ESTEP2")[0] == '1';      // draft switch, see reg_estep2_kernel
+    // HGMM_REG_ESTEP = 1 / 2: the first two generations (A/B switch); default: reg_estep3_kernel
+    static const int gen = getenv("HGMM_REG_ESTEP") ? atoi(getenv("HGMM_REG_ESTEP")) : 3;
+    if (gen >= 3 && t.L <= kRegMaxL) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((n + 127) / 128);
+        cfg.blockDim = dim3(128);
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, reg_estep3_kernel, tx, ty, tz, n, Rt, (const PackedComp*)t.packed, (const float*)t.cplx, t.L, lambda_c,
+                                  racc, want_m2, ctrl);
+    }
+    const bool v2 = gen == 2;
     if (v2) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
@@ -653,8 +788,16 @@ cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, 
 
 cudaError_t launch_reg_solve(const TreeModel& t, double* racc, int zero_after, int solver, double* Rt, double* q_hist,
                              double* qstate, int* ctrl, float tol, cudaStream_t s) {
-    reg_solve_kernel<<<1, 512, 0, s>>>(t, racc, zero_after, solver, Rt, q_hist, qstate, ctrl, tol);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(512);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, reg_solve_kernel, t, racc, zero_after, solver, Rt, q_hist, qstate, ctrl, tol);
 }
 
 void launch_transform_soa(const float* tx, const float* ty, const float* tz, int n, const double* Rt, float* ox, float* oy, float* oz,

@@ -65,8 +65,11 @@ __global__ void tree_pack_all_kernel(TreeModel t) {
     const float* c = t.cov + 9 * j;
     Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
     const double w = t.pi[j];
-    t.cplx[j] = (float)sym3_complexity(s);
-    t.packed[j] = pack_full(w > 0.0 ? log(w) : -INFINITY, t.mu[3 * j], t.mu[3 * j + 1], t.mu[3 * j + 2], s, false, 1e-15);
+    const float cx = (float)sym3_complexity(s);
+    t.cplx[j] = cx;
+    PackedComp pc = pack_full(w > 0.0 ? log(w) : -INFINITY, t.mu[3 * j], t.mu[3 * j + 1], t.mu[3 * j + 2], s, false, 1e-15);
+    pc.pad0 = cx;                     // the registration descent reads the complexity with the parameters (registration.cu)
+    t.packed[j] = pc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -497,7 +500,9 @@ __global__ void tree_cplx_kernel(TreeModel t) {
     if (j >= t.nt) return;
     const float* c = t.cov + 9 * j;
     Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
-    t.cplx[j] = (float)sym3_complexity(s);
+    const float cx = (float)sym3_complexity(s);
+    t.cplx[j] = cx;
+    t.packed[j].pad0 = cx;            // the registration descent reads the complexity with the parameters (registration.cu)
 }
 
 // adaptive build: which nodes of a finished level are terminal (include/hgmm.h, hgmm_tree_config.prune_*)

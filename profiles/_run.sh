@@ -1,10 +1,29 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "config_size" 2>&1 | tail -60) > gpurun_out/r2_t3.log
-grep -E "passed|failed|FAILED" gpurun_out/r2_t3.log
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-(HGMM_TREE_PROF=1 timeout 600 $TR --master-port 29521 profiles/probe_c5_multi.py 1000000 5 4 2>&1 | grep -E "PROBE|PROF|rror") > gpurun_out/r2_c5_n2.log
-(timeout 600 $TR --master-port 29522 profiles/probe_c5_multi.py 1000000 5 4 2>&1 | grep -E "PROBE|PROF|rror") >> gpurun_out/r2_c5_n2.log
-(timeout 300 python profiles/probe_c5_multi.py 1000000 5 4 2>&1 | grep -E "PROBE|PROF|rror") >> gpurun_out/r2_c5_n2.log
-(HGMM_NO_P2P=1 timeout 600 $TR --master-port 29523 profiles/probe_c5_multi.py 1000000 5 3 2>&1 | grep -E "PROBE|PROF|rror") >> gpurun_out/r2_c5_n2.log
-cat gpurun_out/r2_c5_n2.log
+(timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -30) > gpurun_out/r2_all.log
+grep -E "passed|failed|FAILED" gpurun_out/r2_all.log | head -20
+python - <<'PY' > gpurun_out/r2_regab.log 2>&1
+import os, sys, subprocess
+code = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, "."); sys.path.insert(0, "gpu-accelerated-point-cloud-registration-using-hierarchical-gmm_b200")
+import hgmm_b200
+from hgmm_b200 import hgmm as H
+S = np.load("tests/golden/bun000_xyz.npy"); T = np.load("tests/golden/bun045_xyz.npy")
+eng = hgmm_b200.Engine(0)
+for L in (3, 4):
+    init = S[H.reference_init_indices(L)]
+    eng.set_points(torch.from_numpy(S).cuda()); eng.reg_set_target(torch.from_numpy(T).cuda())
+    eng.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False, want_outputs=False)
+    for solver in ("twist_lstsq", "procrustes_svd"):
+        best = 1e9
+        for _ in range(5):
+            rot, t, q, it, _h = eng.register_tree(solver=solver, maxiter=20, tol=0.0)
+            best = min(best, float(eng.last_timing_ms()[0]))
+        print("REG L=%d %s: %d iterations %.3f ms -> %.1f us/iteration  q=%.9g" % (L, solver, it, best, best * 1e3 / it, q))
+'''
+print(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True).stdout)
+PY
+cat gpurun_out/r2_regab.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; echo bench rc=$?
+timeout 120 python __graft_entry__.py smoke 2>&1 | tail -5
