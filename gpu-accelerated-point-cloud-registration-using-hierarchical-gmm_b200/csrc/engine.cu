@@ -247,7 +247,7 @@ int hgmm_create(hgmm_ctx** out, int device, void* stream) {
         cudaHostAlloc((void**)&ctx->h_prog, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&ctx->d_prog, ctx->h_prog, 0) != cudaSuccess ||
         ctx->ctrl.ensure(8 * sizeof(int)) != cudaSuccess ||
-        ctx->qstate.ensure(4 * sizeof(double)) != cudaSuccess || ctx->nchunks.ensure(sizeof(int)) != cudaSuccess ||
+        ctx->qstate.ensure(8 * sizeof(double)) != cudaSuccess || ctx->nchunks.ensure(sizeof(int)) != cudaSuccess ||
         ctx->Rt.ensure(12 * sizeof(double)) != cudaSuccess) {
         hgmm_destroy(ctx);
         return HGMM_ERR_CUDA;
@@ -682,7 +682,7 @@ int hgmm_fit_tree(hgmm_ctx* ctx, const hgmm_tree_config* cfg, const float* init_
         // ctrl[7] (abort) is cleared once per build and is sticky across its levels: after a failed wait on a peer the
         // remaining level kernels return at once instead of each running into the deadline
         CK(cudaMemsetAsync(ctrl, 0, (l == 0 ? 8 : 7) * sizeof(int), s));
-        CK(cudaMemsetAsync(qstate, 0, 4 * sizeof(double), s));
+        CK(cudaMemsetAsync(qstate, 0, 8 * sizeof(double), s));        // [0] prevQ [1] last q, [4..6] the kernel's log-likelihood slots
         CK(cudaMemsetAsync(ctx->gbar.p, 0, 4 * sizeof(unsigned), s));
         CK(cudaMemsetAsync(acc, 0, 2 * stride * sizeof(double), s));
         xh.base = ctx->tepoch;
@@ -1091,7 +1091,9 @@ int hgmm_l2_set_mixtures(hgmm_ctx* ctx, const double* mu_s, const double* phi_s,
                          const double* phi_t, int32_t Jt) {
     if (!ctx) return HGMM_ERR_INVALID;
     if (!mu_s || !phi_s || !mu_t || !phi_t) FAIL(HGMM_ERR_INVALID, "null mixture pointer");
-    if (Js < 1 || Jt < 1 || Js > 65536 || Jt > 65536) FAIL(HGMM_ERR_INVALID, "mixture sizes must be in [1, 65536]");
+    // the cost / BFGS kernels are ONE CTA by design (the whole optimisation in one launch): J x J pairs per evaluation on one SM.
+    // 4096 x 4096 is ~0.1 s per evaluation; the reference's use is J = 100 (gmmreg.py)
+    if (Js < 1 || Jt < 1 || Js > 4096 || Jt > 4096) FAIL(HGMM_ERR_INVALID, "mixture sizes must be in [1, 4096]");
     CK(cudaSetDevice(ctx->device));
     const size_t nd = 4 * (size_t)Js + 4 * (size_t)Jt + 24;
     CK(ctx->l2buf.ensure(nd * sizeof(double)));

@@ -780,7 +780,7 @@ void tree_level_plan(int n, int chunk_points, int level, int num_sms, int smem_o
     const int sc = 96;                                                            // parked fold results (320 B each)
     long long cc = per_cta / chunk_points + (parents + num_sms - 1) / num_sms + 16;      // chunk descriptors kept on chip
     if (cc > 4096) cc = 4096;
-    const long long fixed = (long long)(kTlThreads / 32) * 320 + (long long)sc * 324 + cc * 12;
+    const long long fixed = (long long)(kTlThreads / 32) * (320 + 1280) + (long long)sc * 324 + cc * 12;     // + the transpose buffer
     const long long room = (long long)smem_optin - fixed - 4096;                  // static shared memory of the kernel + slack
     int pc = per_cta;
     if ((long long)pc * 12 > room) pc = 0;                                        // does not fit: stream the points from L2 / HBM

@@ -155,10 +155,11 @@ __device__ __forceinline__ bool cell8_get(const unsigned long long* src, uint32_
 }
 
 // grid barrier: arrival counter that only grows (zeroed by the host before the launch); false when the grid is aborting
-__device__ __forceinline__ bool tl_grid_sync(const TreeLevelArgs& a, unsigned target) {
+__device__ __forceinline__ bool tl_grid_sync(const TreeLevelArgs& a, unsigned target, int* s_nslots) {
     __syncthreads();
     __shared__ int s_ok;
     if (threadIdx.x == 0) {
+        *s_nslots = 0;                                     // the fold stage has been consumed: free for the next E-step
         __threadfence();                                   // this CTA's atomics / stores are visible before it counts as arrived
         atomicAdd(a.gbar, 1u);
         int ok = 1;
@@ -176,12 +177,27 @@ __device__ __forceinline__ bool tl_grid_sync(const TreeLevelArgs& a, unsigned ta
     return s_ok != 0;
 }
 
-__device__ __forceinline__ int tl_lower_bound(const int* __restrict__ starts, int n, long long key) {      // first i with starts[i] >= key
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((long long)__ldg(starts + mid) < key) lo = mid + 1;
-        else hi = mid;
+// first i with starts[i] >= key, searched by a whole warp: 32 probes per round trip (4 rounds for a million chunks instead of
+// 20 dependent loads by one thread -- this sits on the critical path of every level's prologue)
+__device__ __forceinline__ int tl_lower_bound_warp(const int* __restrict__ starts, int n, long long key, int lane) {
+    int lo = 0, hi = n;                                   // answer in [lo, hi]
+    while (hi - lo > 0) {
+        const int span = hi - lo;
+        const int step = (span + 32) / 33;                // probes at lo + (lane + 1) * step - 1, clipped
+        const int pos = min(hi - 1, lo + (lane + 1) * step - 1);
+        const bool below = (long long)__ldg(starts + pos) < key;
+        const unsigned b = __ballot_sync(0xffffffffu, below);
+        const int nb = __popc(b);                         // probes are monotone: the first nb are below the key
+        if (nb == 32) {
+            lo = min(hi, lo + 32 * step);
+        } else {
+            const int first_ge = min(hi - 1, lo + (nb + 1) * step - 1);
+            hi = first_ge;
+            if (nb > 0) lo = min(hi, lo + nb * step);
+        }
+        if (step == 1) {                                  // probes were consecutive: resolved
+            if (nb < 32) { lo = hi; }
+        }
     }
     return lo;
 }
@@ -270,7 +286,8 @@ __global__ void __launch_bounds__(kTlThreads, 1) tree_level_kernel(const TreeLev
     extern __shared__ __align__(16) unsigned char tl_smem[];
     constexpr int W = kTlThreads / 32;
     float* wpar = reinterpret_cast<float*>(tl_smem);                      // [W][80], 16-byte aligned rows
-    float* stage = wpar + W * 80;                                         // [stage_cap][80]
+    float* pkst_all = wpar + W * 80;                                      // [W][320]: parameter transpose of the publishing warps
+    float* stage = pkst_all + W * 32 * kPkWords;                          // [stage_cap][80]
     int* stage_parent = reinterpret_cast<int*>(stage + (size_t)a.stage_cap * 80);
     int* sc_parent = stage_parent + a.stage_cap;
     int* sc_start = sc_parent + a.chunk_cap;
@@ -291,14 +308,14 @@ __global__ void __launch_bounds__(kTlThreads, 1) tree_level_kernel(const TreeLev
 
     // ---------------- prologue: this CTA's run of chunks (balanced by points), its points and descriptors -> shared memory
     const int n_chunks = __ldcg(a.n_chunks_dev);
-    if (tid == 0) {
-        const int c0 = tl_lower_bound(a.chunk_start, n_chunks, (long long)a.n * b / G);
-        const int c1 = (b == G - 1) ? n_chunks : tl_lower_bound(a.chunk_start, n_chunks, (long long)a.n * (b + 1) / G);
-        s_i[0] = c0;
-        s_i[1] = c1;
-        s_i[2] = c0 < n_chunks ? __ldg(a.chunk_start + c0) : a.n;
-        s_i[3] = c1 < n_chunks ? __ldg(a.chunk_start + c1) : a.n;
-        s_nslots = 0;
+    if (warp < 2) {                                       // warps 0 and 1 search the two ends of this CTA's run concurrently
+        const long long key = (long long)a.n * (b + warp) / G;
+        const int c = (warp == 1 && b == G - 1) ? n_chunks : tl_lower_bound_warp(a.chunk_start, n_chunks, key, lane);
+        if (lane == 0) {
+            s_i[warp] = c;
+            s_i[2 + warp] = c < n_chunks ? __ldg(a.chunk_start + c) : a.n;
+            if (warp == 0) s_nslots = 0;
+        }
     }
     __syncthreads();
     const int c0 = s_i[0], c1 = s_i[1], pt0 = s_i[2], pt1 = s_i[3];
@@ -468,22 +485,26 @@ __global__ void __launch_bounds__(kTlThreads, 1) tree_level_kernel(const TreeLev
                 if (run_p >= 0 && run != 0.f) atomicAdd(accp + kAccHdr + (size_t)run_p * (8 * kMom) + k, (double)run);
             }
         }
+        // the level's log-likelihood of this iteration: one of THREE slots (read by every CTA after the barrier, zeroed by CTA 0
+        // two iterations ahead: its last readers are then behind a barrier, its next writers behind another)
+        double* llslot = a.qstate + 4 + (it % 3);
         if (tid == 0) {
             double t = 0.0;
             for (int w = 0; w < W; ++w) t += s_ll[w];
-            if (t != 0.0) atomicAdd(accp, t);
+            if (t != 0.0) atomicAdd(llslot, t);
         }
         // ======================= one grid barrier: every local moment has landed =======================
         TL_STAMP(1);
-        if (!tl_grid_sync(a, (unsigned)(it + 1) * (unsigned)G)) { aborted = true; break; }
-        if (tid == 0) s_nslots = 0;                                       // visible to the next E-step through the verdict's barrier
+        if (!tl_grid_sync(a, (unsigned)(it + 1) * (unsigned)G, &s_nslots)) { aborted = true; break; }
         TL_STAMP(2);
 
         // ======================= exchange + M-step + publish =======================
-        if (b == 0 && tid == 0) {                                         // this rank's log-likelihood -> every rank (own included)
-            const double ql = __ldcg(accp);
-            accp[0] = 0.0;
-            for (int r = 0; r < R; ++r) cell16_put(a.x.ll[r] + (size_t)par * kXchgMaxRanks + me, ql, tag_out);
+        if (b == 0 && tid == 0) {
+            a.qstate[4 + (it + 2) % 3] = 0.0;
+            if (R > 1) {                                                  // this rank's log-likelihood -> every rank (own included)
+                const double ql = __ldcg(llslot);
+                for (int r = 0; r < R; ++r) cell16_put(a.x.ll[r] + (size_t)par * kXchgMaxRanks + me, ql, tag_out);
+            }
         }
         // pass 1: sums of nodes owned elsewhere -> the owner's window (no waiting in this pass).  One cell per thread, consecutive
         // threads on consecutive cells: a warp's store is 512 contiguous bytes on the NVLink, not 32 scattered 8-byte writes
@@ -503,7 +524,7 @@ __global__ void __launch_bounds__(kTlThreads, 1) tree_level_kernel(const TreeLev
         // the CTAs): add the ranks' contributions in rank order, M-step, publish to every rank through a shared-memory
         // transpose so that the 320 parameter cells of the slice leave as contiguous 256-byte stores
         {
-            float* pkst = stage + warp * (32 * kPkWords);                 // the fold stage is idle between the barrier and the next E-step
+            float* pkst = pkst_all + warp * (32 * kPkWords);
             const int n_slices = (a.cnt + 31) >> 5;
             for (int os = warp * G + b; ; os += W * G) {                  // os: index among this rank's slices
                 const int sl = me + R * os;
@@ -550,22 +571,28 @@ __global__ void __launch_bounds__(kTlThreads, 1) tree_level_kernel(const TreeLev
             }
         }
         TL_STAMP(3);
-        // stopping rule: the same R cells, the same order, on every CTA of every rank
-        if (tid == 0) {
-            double q = 0.0;
-            bool ok = true;
-            for (int r = 0; r < R && ok; ++r) {
-                double v[1];
-                ok = cell16_get<1>(a.x.ll[me] + (size_t)par * kXchgMaxRanks + r, tag_out, v, a);
-                q += v[0];
+        // stopping rule.  One rank: every thread reads the slot itself (same value everywhere, no barrier, no broadcast).
+        // Several ranks: the same R cells, summed in the same order, by thread 0 of every CTA of every rank.
+        double q;
+        if (R == 1) {
+            q = __ldcg(llslot);
+        } else {
+            if (tid == 0) {
+                double qq = 0.0;
+                bool ok = true;
+                for (int r = 0; r < R && ok; ++r) {
+                    double v[1];
+                    ok = cell16_get<1>(a.x.ll[me] + (size_t)par * kXchgMaxRanks + r, tag_out, v, a);
+                    qq += v[0];
+                }
+                s_q = qq;
+                s_i[5] = (ok && !tl_abort(a.ctrl)) ? 1 : 0;
             }
-            s_q = q;
-            s_i[5] = (ok && !tl_abort(a.ctrl)) ? 1 : 0;
+            __syncthreads();
+            if (!s_i[5]) { aborted = true; break; }          // CTA-uniform (a thread that failed a poll has set ctrl[7])
+            q = s_q;
         }
-        __syncthreads();
-        if (!s_i[5]) { aborted = true; break; }              // CTA-uniform (a thread that failed a poll has set ctrl[7])
         TL_STAMP(4);
-        const double q = s_q;
         const bool conv = fabs(q - prev_q) < (double)a.ls || it + 1 >= a.max_iters;
         prev_q = q;
         if (!conv) continue;

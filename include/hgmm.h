@@ -185,7 +185,8 @@ int hgmm_register_flat(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, d
  * replaces RigidCostFunction.__call__ / compute_l2_dist  src/python/gmmreg_gpu/cost_functions.py:29-69,
  * GaussTransform.compute src/python/gmmreg_gpu/transforms.py:73-86, diff_rot_from_quaternion src/python/gmmreg_gpu/so.py:4-59
  * and the scipy BFGS call of L2DistRegistration.registration src/python/gmmreg_gpu/gmmreg.py:101-107.
- * mu_* [J,3], phi_* [J] (the reference passes the fitted weights x 1e3); theta = (qw,qx,qy,qz,tx,ty,tz). */
+ * mu_* [J,3], phi_* [J] (the reference passes the fitted weights x 1e3); theta = (qw,qx,qy,qz,tx,ty,tz).
+ * 1 <= J <= 4096 per mixture: the evaluation is a single-CTA kernel (so that a whole BFGS run is one launch). */
 int hgmm_l2_set_mixtures(hgmm_ctx* ctx, const double* mu_source, const double* phi_source, int32_t n_source,
                          const double* mu_target, const double* phi_target, int32_t n_target);
 /* f(theta) and its gradient [7] exactly as the reference's cost function returns them */

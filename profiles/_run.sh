@@ -2,9 +2,13 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 (timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -30) > gpurun_out/r2_all.log
 grep -E "passed|failed|FAILED" gpurun_out/r2_all.log | head -20
-python - <<'PY' > gpurun_out/r2_regab.log 2>&1
-import os, sys, subprocess
-code = r'''
+rm -f gpurun_out/r2_probe5.log
+for cfg in "100000 4 2024 estep" "1000000 5 2025 estep"; do
+  timeout 300 python profiles/probe_tree.py $cfg 4 2>&1 | grep -E "PROBE|PROF|Error|error" >> gpurun_out/r2_probe5.log
+  HGMM_TREE_PROF=1 timeout 300 python profiles/probe_tree.py $cfg 2 2>&1 | grep -E "PROF|Error|error" | tail -1 >> gpurun_out/r2_probe5.log
+done
+cat gpurun_out/r2_probe5.log
+python - <<'PY' 2>&1 | tail -6
 import os, sys, numpy as np, torch
 sys.path.insert(0, "."); sys.path.insert(0, "gpu-accelerated-point-cloud-registration-using-hierarchical-gmm_b200")
 import hgmm_b200
@@ -21,9 +25,4 @@ for L in (3, 4):
             rot, t, q, it, _h = eng.register_tree(solver=solver, maxiter=20, tol=0.0)
             best = min(best, float(eng.last_timing_ms()[0]))
         print("REG L=%d %s: %d iterations %.3f ms -> %.1f us/iteration  q=%.9g" % (L, solver, it, best, best * 1e3 / it, q))
-'''
-print(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True).stdout)
 PY
-cat gpurun_out/r2_regab.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; echo bench rc=$?
-timeout 120 python __graft_entry__.py smoke 2>&1 | tail -5
