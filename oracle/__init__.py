@@ -15,11 +15,15 @@ the reference checkout `/root/reference/`):
                      (`src/python/hgmm/hgmm_cupy_cpu_working.py`, `hgmm_gpu.py`)
 * `registration.py`  tree registration E-step / twist least-squares M-step / outer loop
                      (`src/python/hgmm/hgmm_gpu.py:550-577,620-664,729-768`), the
-                     north-star weighted-Procrustes solve, and the McAdams 3x3 SVD
-                     (`src/c++/common/svd3.h`)
+                     north-star weighted-Procrustes solve, the flat-mixture registration of BASELINE
+                     configs[3] (no reference implementation: gmm_reg.cu:54-56 is empty), and the McAdams
+                     3x3 SVD (`src/c++/common/svd3.h`)
 * `l2reg.py`         L2-distance cost/gradient of the flat registration
                      (`src/python/gmmreg_gpu/cost_functions.py`, `so.py`, `transforms.py`)
-* `synth.py`         synthetic LiDAR / surface generators
+* `synth.py`         alias of `hgmm_b200/synth.py` (the synthetic LiDAR / surface INPUT generators of SURVEY.md section 8d live
+                     with the package: bench.py and the probes use them without touching this directory)
+* `make_golden_lidar.py`  config-size tree fixtures: this oracle run once on the 100k / 50k LiDAR workloads
+                     (`tests/golden/tree_build_lidar*`)
 * `c/`               plain-C (OpenMP) restatement of the same E/M arithmetic used as the
                      timed CPU baseline; built into `oracle/_build/`
 * `refshim/`, `make_golden.py`  harness that imports the *unmodified* reference Python
