@@ -14,6 +14,8 @@
 // parameters sit in 384 B of shared memory, each lane walks its points keeping all 8 x 10 centred
 // moments in registers, a butterfly reduce-scatter folds the warp, and 80 fp64 atomics per chunk
 // land in the level's moment block.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -788,6 +790,15 @@ void tree_level_plan(int n, int chunk_points, int level, int num_sms, int smem_o
     *chunk_cap = (int)cc;
     *stage_cap = sc;
     *smem_bytes = (size_t)fixed + (size_t)pc * 12;
+    // test switch (read per call, tests/test_gpu_parity.py): force the kernel's overflow paths, which configs of ordinary size
+    // never reach -- bit 0: points streamed from L2 instead of shared memory; bit 1: chunk descriptors read from global memory;
+    // bit 2: a two-slot fold stage (every further fold goes straight to L2 atomics)
+    if (const char* e = getenv("HGMM_TREE_FORCE")) {
+        const int f = atoi(e);
+        if (f & 1) { *smem_bytes -= (size_t)*pt_cap * 12; *pt_cap = 0; }
+        if (f & 2) *chunk_cap = 1;
+        if (f & 4) *stage_cap = 2;
+    }
 }
 
 // one cooperative launch for the whole EM loop of a level (tree_level.cuh)

@@ -599,8 +599,16 @@ __global__ void __launch_bounds__(kTlThreads, 1) tree_level_kernel(const TreeLev
 
         // ======================= converged: leave the level with the full replicated model =======================
         if (R > 1) {
-            for (int j = tid * G + b; j < a.cnt; j += kTlThreads * G) {      // owners publish (pi, mu, Sigma) to the peers
-                if ((j >> 5) % R != me) continue;
+            // owners publish (pi, mu, Sigma) to the peers -- with the SAME slice -> warp mapping as the M-step above, so every lane
+            // re-reads what it wrote itself.  (Any other mapping reads t.pi / t.mu / t.cov of a slice another CTA may still be
+            // computing: the peers then install the previous iteration's parameters for it -- seen at 8 ranks as a 1e-2 error
+            // below the root level while the root, owned by the reporting rank, was exact.)
+            const int n_slices = (a.cnt + 31) >> 5;
+            for (int os = warp * G + b; ; os += W * G) {
+                const int sl = me + R * os;
+                if (sl >= n_slices) break;
+                const int j = sl * 32 + lane;
+                if (j >= a.cnt) continue;
                 const int g = a.lb + j;
                 const float* c = a.t.cov + 9 * (size_t)g;
                 const float f[kFinWords] = {a.t.pi[g], a.t.mu[3 * g], a.t.mu[3 * g + 1], a.t.mu[3 * g + 2], c[0], c[1], c[2], c[4], c[5], c[8]};

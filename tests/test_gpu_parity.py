@@ -3,6 +3,8 @@
 Tolerance (BASELINE.json north_star): fitted mu / Sigma / pi and the recovered SE(3) within 1e-4
 relative Frobenius of the reference semantics (float64 oracle, pinned to the unmodified reference by
 oracle/make_golden.py).  Where the oracle is slow, size-independent properties are checked instead."""
+import os
+
 import numpy as np
 import pytest
 
@@ -531,6 +533,46 @@ def test_adaptive_tree_build_matches_oracle(engine, bun000):
     engine.reg_set_target((X[::2] @ Rz.T + np.array([0.002, 0.001, -0.001])).astype(np.float32))
     rot, t, q, it, _ = engine.register_tree(solver="twist_lstsq", maxiter=20, tol=1e-6, lambda_c=0.02)
     assert rel_fro(rot, Rz.T) < 2e-2
+
+
+@pytest.mark.parametrize("force", [1, 2, 4, 7])
+def test_tree_level_kernel_overflow_paths(engine, bun000, force):
+    """the persistent level kernel keeps its points, chunk descriptors and fold results on chip -- up to capacities that clouds of
+    ordinary size never exceed.  HGMM_TREE_FORCE shrinks them (bit 0: points streamed from L2, bit 1: descriptors from global
+    memory, bit 2: a two-slot fold stage, the rest goes straight to L2 atomics): the fallback paths must give the same tree."""
+    from oracle import hgmm_tree
+    X = bun000[::2]
+    L = 3
+    init = X[hgmm_tree.reference_init_indices(L)]
+    engine.set_points(X)
+    kw = dict(ls=0.0, ld=1e-4, sig2=4e-4, ll_mode="estep", max_iters_per_level=10)
+    ref = engine.fit_tree(init, L, **kw)
+    os.environ["HGMM_TREE_FORCE"] = str(force)
+    try:
+        r = engine.fit_tree(init, L, **kw)
+    finally:
+        del os.environ["HGMM_TREE_FORCE"]
+    assert r["iters"].tolist() == ref["iters"].tolist()
+    assert rel_fro(r["pi"], ref["pi"]) < 1e-5 and rel_fro(r["mu"], ref["mu"]) < 1e-5 and rel_fro(r["cov"], ref["cov"]) < 1e-5
+    assert float((r["current"] == ref["current"]).mean()) > 0.9999
+
+
+def test_tree_more_nodes_than_points(engine, bun000):
+    """ragged extreme: 300 points under a depth-3 tree (584 nodes, 512 leaves): most nodes stay blank, nothing may go NaN, and the
+    result must still equal the oracle's"""
+    from oracle import hgmm_tree
+    X = bun000[::134][:300]
+    L = 3
+    init = np.resize(X, (hgmm_tree.n_total(L), 3))[hgmm_tree.reference_init_indices(L) % len(X)]
+    engine.set_points(X)
+    r = engine.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep")
+    opi, omu, ocov, ocur, oit, _ = hgmm_tree.build_gmm_tree(X, L, 20.0, 1e-4, init.astype(np.float64), sig2=np.float32(4e-4), ll_mode="estep",
+                                                            return_trace=True)
+    assert np.isfinite(r["mu"]).all() and np.isfinite(r["cov"]).all()
+    assert r["iters"].tolist() == list(oit)
+    assert rel_fro(r["pi"], opi) < TOL and float((r["current"] == ocur).mean()) == 1.0
+    live = (opi > 0) & (r["pi"] > 0)
+    assert rel_fro(r["mu"][live], omu[live]) < TOL and rel_fro(r["cov"][live], ocov[live]) < 1e-3      # single-point nodes: Sigma = 0 +- rounding
 
 
 def _tree_level_errors(r, g, lv):

