@@ -163,6 +163,7 @@ struct hgmm_ctx {
     bool p2p_ready = false;
     uint32_t xepoch = 0;
     int xwin_tree_levels = 0;             // deepest tree the window's tree region was sized for (0: none)
+    size_t xwin_reg_off = 0;              // byte offset of the tree-registration region in the window (0: none)
     double xchg_timeout_s = 30.0;         // deadline of every in-kernel wait on a peer (HGMM_XCHG_TIMEOUT_S)
 };
 
@@ -922,7 +923,7 @@ int hgmm_reg_mstep(hgmm_ctx* ctx, int32_t solver, double* rot, double* t, double
     CK(cudaMemsetAsync(ctx->ctrl.p, 0, 8 * sizeof(int), s));
     CK(cudaMemsetAsync(ctx->qstate.p, 0, 4 * sizeof(double), s));
     CK(launch_reg_solve(ctx->tm, ctx->racc.as<double>(), 0, solver, ctx->Rt.as<double>(), ctx->hist.as<double>(),
-                        ctx->qstate.as<double>(), ctx->ctrl.as<int>(), 0.f, s));
+                        ctx->qstate.as<double>(), ctx->ctrl.as<int>(), 0.f, nullptr, s));      // hgmm_reg_estep has already summed the ranks
     ctx->launches += 1;
     CK(cudaMemcpyAsync(ctx->h_dbl, ctx->Rt.p, 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_dbl + 16, ctx->qstate.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -967,6 +968,20 @@ int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, d
     CK(cudaMemsetAsync(ctx->qstate.p, 0, 4 * sizeof(double), s));
     CK(cudaMemsetAsync(ctx->racc.p, 0, rn * sizeof(double), s));
     CK(cudaEventRecord(ctx->ev0, s));
+    // several ranks with peer-memory windows: the ranks' moments are exchanged INSIDE the solve kernel (registration.cu:
+    // reg_gather_node) -- two PDL-chained launches per iteration at any N, no ncclAllReduce.  Deeper trees than the region holds,
+    // ranks without windows and HGMM_REG_NO_P2P=1 keep the collective.
+    static const bool reg_no_p2p = getenv("HGMM_REG_NO_P2P") && getenv("HGMM_REG_NO_P2P")[0] == '1';
+    RegXchgView xv = {};
+    xv.nranks = 1;
+    const bool fused = ctx->nranks > 1 && ctx->p2p_ready && ctx->xwin_reg_off != 0 && tm.nt <= kRegXchgNodes && !reg_no_p2p;
+    if (fused) {
+        for (int q = 0; q < ctx->nranks; ++q) xv.data[q] = reinterpret_cast<uint4*>(static_cast<char*>(ctx->xpeer[q]) + ctx->xwin_reg_off);
+        xv.rank = ctx->rank; xv.nranks = ctx->nranks;
+        xv.base = ctx->tepoch;
+        ctx->tepoch += (uint32_t)cfg->maxiter + 2u;
+        xv.timeout_ns = (unsigned long long)(ctx->xchg_timeout_s * 1e9);
+    }
     const int batch = 4;
     int issued = 0;
     bool done = false;
@@ -975,15 +990,18 @@ int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, d
             // the solve kernel zeroes the moments it consumed, so no separate clearing launch is needed per iteration
             CK(launch_reg_estep(ctx->tx.as<float>(), ctx->ty.as<float>(), ctx->tz.as<float>(), ctx->nt_pts, ctx->Rt.as<double>(), tm,
                                 cfg->lambda_c, ctx->racc.as<double>(), 0, ctrl, s));
-            r = allreduce(ctx, ctx->racc.as<double>(), rn);
-            if (r != HGMM_OK) return r;
+            if (!fused) {
+                r = allreduce(ctx, ctx->racc.as<double>(), rn);
+                if (r != HGMM_OK) return r;
+            }
             CK(launch_reg_solve(tm, ctx->racc.as<double>(), 1, cfg->solver, ctx->Rt.as<double>(), ctx->hist.as<double>(),
-                                ctx->qstate.as<double>(), ctrl, cfg->tol, s));
+                                ctx->qstate.as<double>(), ctrl, cfg->tol, fused ? &xv : nullptr, s));
             ctx->launches += 2;
         }
-        CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_ctrl, ctrl, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         done = ctx->h_ctrl[0] != 0;
+        if (ctx->h_ctrl[7]) FAIL(HGMM_ERR_NCCL, "registration: a wait on a peer rank timed out (rank missing, or the ranks' call sequences differ)");
     }
     CK(cudaEventRecord(ctx->ev1, s));
     const int iters = ctx->h_ctrl[1];
@@ -1225,11 +1243,14 @@ int hgmm_p2p_export(hgmm_ctx* ctx, void* out_handle64) {
         if (const char* e = getenv("HGMM_P2P_TREE_LEVELS")) lv = atoi(e);
         if (lv < 0) lv = 0;
         if (lv > 6) lv = 6;
-        const size_t bytes = kXchgBytes + (lv > 0 ? tree_win_layout(lv).bytes : 0);
+        const size_t tree_bytes = (lv > 0 ? tree_win_layout(lv).bytes : 0);
+        const size_t reg_off = (kXchgBytes + tree_bytes + 255) / 256 * 256;
+        const size_t bytes = reg_off + kRegXchgBytes;                   // + the tree-registration region (12 MB)
         CK(cudaMalloc(&ctx->xwin, bytes));
         CK(cudaMemset(ctx->xwin, 0, bytes));
         CK(cudaDeviceSynchronize());
         ctx->xwin_tree_levels = lv;
+        ctx->xwin_reg_off = reg_off;
     }
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, ctx->xwin));

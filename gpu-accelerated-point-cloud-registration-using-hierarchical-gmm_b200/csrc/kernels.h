@@ -62,6 +62,18 @@ struct XchgView {
     unsigned long long timeout_ns;               // deadline of a wait on a peer
 };
 
+// tree-registration exchange (registration.cu: reg_solve_kernel): every rank's (M0, M1) of every node as 16-byte cells
+// [2 parities][ranks][kRegXchgNodes * 4]; sized for depth <= 4 (4680 nodes), deeper trees keep ncclAllReduce
+constexpr int kRegXchgNodes = 4680;
+constexpr size_t kRegXchgCells = (size_t)2 * kXchgMaxRanks * kRegXchgNodes * 4;
+constexpr size_t kRegXchgBytes = kRegXchgCells * 16;
+struct RegXchgView {
+    uint4* data[kXchgMaxRanks];                  // rank r's region as mapped here (own entry: the local pointer); all null = no exchange
+    int rank, nranks;
+    uint32_t base;                               // tag of iteration it is base + it + 1
+    unsigned long long timeout_ns;
+};
+
 struct TreeModel {
     int L;                     // levels
     int nt;                    // total nodes 8(8^L-1)/7
@@ -199,7 +211,7 @@ cudaError_t launch_root_chunks(TreeWork& w, int n, const PartitionScratch& ps, i
 cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, int n, const double* Rt, const TreeModel& t,
                              float lambda_c, double* racc, int want_m2, const int* ctrl, cudaStream_t s);
 cudaError_t launch_reg_solve(const TreeModel& t, double* racc, int zero_after, int solver, double* Rt, double* q_hist,
-                             double* qstate, int* ctrl, float tol, cudaStream_t s);
+                             double* qstate, int* ctrl, float tol, const RegXchgView* xv, cudaStream_t s);
 void launch_transform_soa(const float* tx, const float* ty, const float* tz, int n, const double* Rt, float* ox, float* oy, float* oz,
                           const int* ctrl, cudaStream_t s);
 cudaError_t launch_reg_flat_solve(const FlatModel& m, const double* acc, int solver, double* Rt, double* q_hist, double* qstate,

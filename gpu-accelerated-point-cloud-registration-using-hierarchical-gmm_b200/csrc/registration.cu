@@ -581,23 +581,91 @@ __device__ __forceinline__ void procrustes_finish(const double* v, double* Rt, d
     ctrl[1] = it + 1;
 }
 
-// ctrl: [0] done, [1] iterations, [2] numeric failure flag.  qstate: [0] previous q, [1] last q, [2] has-previous flag
+// ---- multi-GPU: the ranks' (M0, M1) of node i, exchanged over peer memory INSIDE the solve kernel (no ncclAllReduce, no third
+// launch).  The thread that owns node i stores this rank's four sums into every peer's region as self-validating 16-byte cells
+// (fp64 as two (half, tag) words, tag = base + iteration + 1), polls its own region for the peers' cells of the same node, and adds
+// the R contributions in rank order (own from registers): every rank ends with bit-identical sums, hence bit-identical transforms
+// and the same stopping decision.  Two parities: a rank's next push needs every peer's current one.
+__device__ __forceinline__ void reg_cell_put(uint4* cell, double v, uint32_t tag) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(cell), "r"((uint32_t)u), "r"(tag) : "memory");
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<char*>(cell) + 8), "r"((uint32_t)(u >> 32)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ bool reg_gather_node(const RegXchgView& xv, int node, int par, uint32_t tag, double* A /*[4] in: own, out: sum*/,
+                                                int* ctrl) {
+    const int R = xv.nranks, me = xv.rank;
+    const size_t half = (size_t)kXchgMaxRanks * kRegXchgNodes * 4;
+    for (int r = 0; r < R; ++r) {
+        if (r == me) continue;
+        uint4* dst = xv.data[r] + (size_t)par * half + ((size_t)me * kRegXchgNodes + node) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) reg_cell_put(dst + k, A[k], tag);
+    }
+    double S[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned long long t0 = 0ull;
+    for (int r = 0; r < R; ++r) {
+        if (r == me) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) S[k] += A[k];
+            continue;
+        }
+        const uint4* src = xv.data[me] + (size_t)par * half + ((size_t)r * kRegXchgNodes + node) * 4;
+        unsigned spins = 0;
+        for (;;) {
+            uint4 c[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c[k].x), "=r"(c[k].y), "=r"(c[k].z), "=r"(c[k].w) : "l"(src + k) : "memory");
+            bool all = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) all = all && c[k].y == tag && c[k].w == tag;
+            if (all) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) S[k] += __longlong_as_double((long long)(((unsigned long long)c[k].z << 32) | c[k].x));
+                break;
+            }
+            if ((++spins & 255u) == 0u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0ull) t0 = now;
+                int bad;
+                asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(bad) : "l"(ctrl + 7) : "memory");
+                if (bad || now - t0 > xv.timeout_ns) {
+                    atomicExch(ctrl + 7, 1);
+                    return false;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) A[k] = S[k];
+    return true;
+}
+
+// ctrl: [0] done, [1] iterations, [2] numeric failure flag, [7] a wait on a peer timed out.
+// qstate: [0] previous q, [1] last q, [2] has-previous flag
 __global__ void __launch_bounds__(512) reg_solve_kernel(TreeModel t, double* __restrict__ racc, int zero_after, int solver,
                                                         double* __restrict__ Rt, double* __restrict__ q_hist,
-                                                        double* __restrict__ qstate, int* __restrict__ ctrl, float tol) {
+                                                        double* __restrict__ qstate, int* __restrict__ ctrl, float tol, RegXchgView xv) {
     asm volatile("griddepcontrol.wait;" ::: "memory");        // PDL-chained with the E-step (all of its atomics have landed)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (ctrl[0]) return;
     __shared__ double sm[16 * kSys];
     const int tid = threadIdx.x, nth = blockDim.x;
     const double f32eps = 1.1920928955078125e-07;            // np.finfo(np.float32).eps  (hgmm_gpu.py:741)
+    const bool xchg = xv.nranks > 1;
+    const int x_it = ctrl[1], x_par = x_it & 1;
+    const uint32_t x_tag = xv.base + (uint32_t)x_it + 1u;
     if (solver == HGMM_SOLVER_TWIST_LSTSQ) {
         double v[kSys];
         for (int k = 0; k < kSys; ++k) v[k] = 0.0;
         for (int i = tid; i < t.nt; i += nth) {
             double* A = racc + (size_t)i * kRegMom;
-            const double M0 = A[0], S1x = A[1], S1y = A[2], S1z = A[3];
+            double G4[4] = {A[0], A[1], A[2], A[3]};
             if (zero_after) { A[0] = 0.0; A[1] = 0.0; A[2] = 0.0; A[3] = 0.0; }
+            if (xchg && !reg_gather_node(xv, i, x_par, x_tag, G4, ctrl)) break;
+            const double M0 = G4[0], S1x = G4[1], S1y = G4[2], S1z = G4[3];
             if (M0 < f32eps) continue;
             const float* c = t.cov + 9 * i;
             Sym3 s{c[0], 0.5 * ((double)c[1] + c[3]), 0.5 * ((double)c[2] + c[6]), c[4], 0.5 * ((double)c[5] + c[7]), c[8]};
@@ -628,8 +696,10 @@ __global__ void __launch_bounds__(512) reg_solve_kernel(TreeModel t, double* __r
         for (int k = 0; k < kPro; ++k) v[k] = 0.0;
         for (int i = tid; i < t.nt; i += nth) {
             double* A = racc + (size_t)i * kRegMom;
-            const double w = A[0], S1x = A[1], S1y = A[2], S1z = A[3];
+            double G4[4] = {A[0], A[1], A[2], A[3]};
             if (zero_after) { A[0] = 0.0; A[1] = 0.0; A[2] = 0.0; A[3] = 0.0; }
+            if (xchg && !reg_gather_node(xv, i, x_par, x_tag, G4, ctrl)) break;
+            const double w = G4[0], S1x = G4[1], S1y = G4[2], S1z = G4[3];
             if (w < f32eps) continue;
             const double s[3] = {S1x / w, S1y / w, S1z / w};
             const double m[3] = {t.mu[3 * i], t.mu[3 * i + 1], t.mu[3 * i + 2]};
@@ -787,7 +857,10 @@ cudaError_t launch_reg_estep(const float* tx, const float* ty, const float* tz, 
 }
 
 cudaError_t launch_reg_solve(const TreeModel& t, double* racc, int zero_after, int solver, double* Rt, double* q_hist,
-                             double* qstate, int* ctrl, float tol, cudaStream_t s) {
+                             double* qstate, int* ctrl, float tol, const RegXchgView* xvp, cudaStream_t s) {
+    RegXchgView xv = {};
+    xv.nranks = 1;
+    if (xvp) xv = *xvp;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(1);
     cfg.blockDim = dim3(512);
@@ -797,7 +870,7 @@ cudaError_t launch_reg_solve(const TreeModel& t, double* racc, int zero_after, i
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, reg_solve_kernel, t, racc, zero_after, solver, Rt, q_hist, qstate, ctrl, tol);
+    return cudaLaunchKernelEx(&cfg, reg_solve_kernel, t, racc, zero_after, solver, Rt, q_hist, qstate, ctrl, tol, xv);
 }
 
 void launch_transform_soa(const float* tx, const float* ty, const float* tz, int n, const double* Rt, float* ox, float* oy, float* oz,

@@ -64,6 +64,11 @@ def main():
     T = (X @ R.T + np.array([0.002, -0.001, 0.003])).astype(np.float32)
     eng.reg_set_target(hd.shuffled_shard(T, rank, world, seed=6))
     rot, t, q, it, _ = eng.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+    # ---- the same registration against an IDENTICAL model on both sides (the sharded tree installed everywhere): isolates the
+    #      registration's own exchange (fused into the solve kernel over peer memory) from the tree's amplified differences
+    eng.tree_set_model(L, tre["pi"], tre["mu"], tre["cov"])
+    rot_s, t_s, q_s, it_s, _ = eng.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+    rot_p, t_p, q_p, it_p, _ = eng.register_tree(solver="procrustes_svd", maxiter=15, tol=1e-9)
     # ---- flat-mixture registration with a sharded target (model: a J = 100 fit of the sharded source)
     Jr = 100
     mur = X[np.random.default_rng(4).choice(len(X), Jr, replace=False)]
@@ -91,6 +96,9 @@ def main():
         tse = ref.fit_tree(init, L, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False)
         ref.reg_set_target(T)
         rot1, t1, q1, it1, _ = ref.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+        ref.tree_set_model(L, tre["pi"], tre["mu"], tre["cov"])
+        rot_s1, t_s1, q_s1, it_s1, _ = ref.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+        rot_p1, t_p1, q_p1, it_p1, _ = ref.register_tree(solver="procrustes_svd", maxiter=15, tol=1e-9)
         ref.fit_flat(mur, covr, wr, cov_type="full", max_iter=10, want_outputs=False)
         frot1, ft1, fq1, fit1, _ = ref.register_flat(solver="procrustes_svd", maxiter=15, tol=1e-9)
         s4 = ref.fit_tree(init4, L4, ls=0.0, ld=1e-4, sig2=4e-4, ll_mode="estep", max_iters_per_level=6, want_current=False)
@@ -121,6 +129,8 @@ def main():
             "flat_full": max(rel_fro(r["means"], s["means"]), rel_fro(r["covs"], s["covs"]), rel_fro(r["weights"], s["weights"]), rel_fro(r["ll"], s["ll"])),
             "flat_diag": max(rel_fro(rd["means"], sd["means"]), rel_fro(rd["covs"], sd["covs"]), rel_fro(rd["weights"], sd["weights"])),
             "flat_reg": max(rel_fro(frot, frot1), float(np.abs(ft - ft1).max())),
+            "tree_reg_same_model_twist": max(rel_fro(rot_s, rot_s1), float(np.abs(t_s - t_s1).max())),
+            "tree_reg_same_model_procrustes": max(rel_fro(rot_p, rot_p1), float(np.abs(t_p - t_p1).max())),
             "tree_level_root": root(tr, ts), "tree_estep_root": root(tre, tse), "tree_estep_nccl_root": root(tren, tse), "tree_L4_fixed6_root": root(t4, s4),
         }
         soft = {      # converged / deep trees below the root: a point that changes leaf on the last bit of a responsibility moves a small node by
@@ -139,7 +149,7 @@ def main():
               tre["iters"].tolist(), tse["iters"].tolist(), it, it1, flush=True)
         ok = all(v < 1e-4 for v in errs.values()) and all(v < 5e-2 for v in soft.values()) and unweighted["reg_on_the_sharded_tree"] < 2e-2
         ok = ok and tr["iters"].tolist()[:2] == ts["iters"].tolist()[:2] and tre["iters"].tolist()[:2] == tse["iters"].tolist()[:2]
-        ok = ok and fit_ == fit1 and t4["iters"].tolist() == s4["iters"].tolist() == [6] * L4
+        ok = ok and fit_ == fit1 and t4["iters"].tolist() == s4["iters"].tolist() == [6] * L4 and it_s == it_s1 and it_p == it_p1
         ref.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
