@@ -719,6 +719,10 @@ def parity_vs_single(eng, world, rank, local):
     T = (X @ R.T + np.array([0.002, -0.001, 0.003])).astype(np.float32)
     eng.reg_set_target(hdist.shuffled_shard(T, rank, world, seed=6))
     rot, t, q, it, _ = eng.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+    # the same registration against an IDENTICAL model on both sides (the sharded tree -- bit-identical on every rank -- installed
+    # on the single-GPU engine too): isolates the registration's own exchange from the tree's amplified differences
+    eng.tree_set_model(L, t_est["pi"], t_est["mu"], t_est["cov"])
+    rot_m, t_m, q_m, it_m, _ = eng.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
     t_lvl = eng.fit_tree(init, L, ll_mode="level", **tkw)
     Jr = 100
     mur, covr, wr = init_model(X, seed=4, j=Jr)
@@ -733,6 +737,8 @@ def parity_vs_single(eng, world, rank, local):
         s_fix = ref.fit_tree(init, L, ls=0.0, ld=1e-4, sig2=4e-4, ll_mode="estep", max_iters_per_level=6, want_current=False)
         ref.reg_set_target(T)
         rot1, t1, q1, it1, _ = ref.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+        ref.tree_set_model(L, t_est["pi"], t_est["mu"], t_est["cov"])
+        rot_m1, t_m1, q_m1, it_m1, _ = ref.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
         s_lvl = ref.fit_tree(init, L, ll_mode="level", **tkw)
         ref.fit_flat(mur, covr, wr, cov_type="full", max_iter=10, want_outputs=False)
         frot1, ft1, fq1, fit1, _ = ref.register_flat(solver="procrustes_svd", maxiter=15, tol=1e-9)
@@ -746,6 +752,7 @@ def parity_vs_single(eng, world, rank, local):
             "tree_L3_ll_estep_root_level": tree_distance(t_est, s_est, L)["root_level_rel_fro"],
             "tree_L3_ll_level_root_level": tree_distance(t_lvl, s_lvl, L)["root_level_rel_fro"],
             "flat_registration": max(rel_fro(frot, frot1), float(np.abs(ft - ft1).max())),
+            "tree_registration_same_model": max(rel_fro(rot_m, rot_m1), float(np.abs(t_m - t_m1).max())),
         }
         # reported, held to the mass-weighted bound: the converged trees below the root (a point that changes leaf on the last bit
         # of a responsibility moves a small node by 1e-2) and the registration against that tree
@@ -755,12 +762,13 @@ def parity_vs_single(eng, world, rank, local):
                 "tree_L3_ll_level_mass_weighted": tree_distance(t_lvl, s_lvl, L)["worst_mass_weighted_mu_error"],
                 "tree_registration_on_the_sharded_tree": max(rel_fro(rot, rot1), float(np.abs(t - t1).max()))}
         iters_equal = bool(t_est["iters"].tolist()[:2] == s_est["iters"].tolist()[:2] and t_lvl["iters"].tolist()[:2] == s_lvl["iters"].tolist()[:2]
-                           and fit_ == fit1 and t_fix["iters"].tolist() == s_fix["iters"].tolist())
+                           and fit_ == fit1 and it_m == it_m1 and t_fix["iters"].tolist() == s_fix["iters"].tolist())
         out = {"max_rel_fro": errs, "amplified_quantities": soft, "iters_equal": iters_equal, "tolerance": PARITY_TOL, "peer_memory": bool(p2p_on),
                "iters": {"tree_estep": [t_est["iters"].tolist(), s_est["iters"].tolist()], "tree_level": [t_lvl["iters"].tolist(), s_lvl["iters"].tolist()],
-                         "tree_registration": [int(it), int(it1)], "flat_registration": [int(fit_), int(fit1)]},
+                         "tree_registration": [int(it), int(it1)], "tree_registration_same_model": [int(it_m), int(it_m1)],
+                         "flat_registration": [int(fit_), int(fit1)]},
                "cloud": "every 2nd bun000 vertex (20128 pts), shards of a seeded shuffle", "ok": bool(max(errs.values()) < PARITY_TOL and iters_equal and soft["tree_L3_ll_estep_mass_weighted"] < 5e-2 and
-                          soft["tree_L3_ll_level_mass_weighted"] < 5e-2 and soft["tree_registration_on_the_sharded_tree"] < 2e-2)}
+                          soft["tree_L3_ll_level_mass_weighted"] < 5e-2)}
     return out if rank == 0 else {"ok": True}
 
 

@@ -240,10 +240,15 @@ __device__ __forceinline__ void reg_accumulate_level(int key, float gam, float x
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
         }
-        if (lane == leader) {
-            double* A = k < kTopNodes ? &s_acc[k][0] : racc + (size_t)k * kRegMom;
+        if (lane == leader) {                                   // two branches, not one generic pointer: the global adds are then
+            if (k < kTopNodes) {                                // native RED.ADD.F64 instead of a generic-address CAS loop
 #pragma unroll
-            for (int i = 0; i < NM; ++i) atomicAdd(A + i, v[i]);
+                for (int i = 0; i < NM; ++i) atomicAdd(&s_acc[k][i], v[i]);
+            } else {
+                double* A = racc + (size_t)k * kRegMom;
+#pragma unroll
+                for (int i = 0; i < NM; ++i) atomicAdd(A + i, v[i]);
+            }
         }
         todo &= ~__ballot_sync(0xffffffffu, mine);
     }
@@ -586,14 +591,16 @@ __device__ __forceinline__ void procrustes_finish(const double* v, double* Rt, d
 // (fp64 as two (half, tag) words, tag = base + iteration + 1), polls its own region for the peers' cells of the same node, and adds
 // the R contributions in rank order (own from registers): every rank ends with bit-identical sums, hence bit-identical transforms
 // and the same stopping decision.  Two parities: a rank's next push needs every peer's current one.
+// The cells are self-validating (every 8-byte word carries the tag), so the stores need no ordering among themselves: relaxed
+// system-scope stores can be posted back to back, where st.volatile keeps a thread's stores in program order.
 __device__ __forceinline__ void reg_cell_put(uint4* cell, double v, uint32_t tag) {
     const unsigned long long u = (unsigned long long)__double_as_longlong(v);
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(cell), "r"((uint32_t)u), "r"(tag) : "memory");
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<char*>(cell) + 8), "r"((uint32_t)(u >> 32)), "r"(tag)
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(cell), "r"((uint32_t)u), "r"(tag) : "memory");
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<char*>(cell) + 8), "r"((uint32_t)(u >> 32)), "r"(tag)
                  : "memory");
 }
-__device__ __forceinline__ bool reg_gather_node(const RegXchgView& xv, int node, int par, uint32_t tag, double* A /*[4] in: own, out: sum*/,
-                                                int* ctrl) {
+// push this rank's four sums of `node` into every peer's region (all of a thread's nodes are pushed before it waits for any)
+__device__ __forceinline__ void reg_push_node(const RegXchgView& xv, int node, int par, uint32_t tag, const double* A) {
     const int R = xv.nranks, me = xv.rank;
     const size_t half = (size_t)kXchgMaxRanks * kRegXchgNodes * 4;
     for (int r = 0; r < R; ++r) {
@@ -602,6 +609,11 @@ __device__ __forceinline__ bool reg_gather_node(const RegXchgView& xv, int node,
 #pragma unroll
         for (int k = 0; k < 4; ++k) reg_cell_put(dst + k, A[k], tag);
     }
+}
+__device__ __forceinline__ bool reg_gather_node(const RegXchgView& xv, int node, int par, uint32_t tag, double* A /*[4] in: own, out: sum*/,
+                                                int* ctrl) {
+    const int R = xv.nranks, me = xv.rank;
+    const size_t half = (size_t)kXchgMaxRanks * kRegXchgNodes * 4;
     double S[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned long long t0 = 0ull;
     for (int r = 0; r < R; ++r) {
@@ -657,6 +669,8 @@ __global__ void __launch_bounds__(512) reg_solve_kernel(TreeModel t, double* __r
     const bool xchg = xv.nranks > 1;
     const int x_it = ctrl[1], x_par = x_it & 1;
     const uint32_t x_tag = xv.base + (uint32_t)x_it + 1u;
+    if (xchg)                                                 // one NVLink hop for the whole tree: push everything, then collect
+        for (int i = tid; i < t.nt; i += nth) reg_push_node(xv, i, x_par, x_tag, racc + (size_t)i * kRegMom);
     if (solver == HGMM_SOLVER_TWIST_LSTSQ) {
         double v[kSys];
         for (int k = 0; k < kSys; ++k) v[k] = 0.0;
