@@ -968,10 +968,13 @@ int hgmm_register_tree(hgmm_ctx* ctx, const hgmm_reg_config* cfg, double* rot, d
     CK(cudaMemsetAsync(ctx->qstate.p, 0, 4 * sizeof(double), s));
     CK(cudaMemsetAsync(ctx->racc.p, 0, rn * sizeof(double), s));
     CK(cudaEventRecord(ctx->ev0, s));
-    // several ranks with peer-memory windows: the ranks' moments are exchanged INSIDE the solve kernel (registration.cu:
-    // reg_gather_node) -- two PDL-chained launches per iteration at any N, no ncclAllReduce.  Deeper trees than the region holds,
-    // ranks without windows and HGMM_REG_NO_P2P=1 keep the collective.
-    static const bool reg_no_p2p = getenv("HGMM_REG_NO_P2P") && getenv("HGMM_REG_NO_P2P")[0] == '1';
+    // several ranks: the ranks' moments are all-reduced between the E-step and the solve (ncclAllReduce, 61.9 us/iteration at
+    // N = 8 on the L3 bunny tree).  HGMM_REG_P2P=1 (read per call) exchanges them INSIDE the solve kernel over the peer-memory
+    // windows instead (registration.cu: reg_gather_node; two PDL-chained launches per iteration, no NCCL call): bit-identical
+    // results, but the all-to-all is pushed by the solve kernel's single CTA and measures 52.3 vs 49.5 us/iteration at N = 2
+    // and 97.3 vs 61.9 at N = 8 (profiles/r02_multigpu_n8_test.txt), so it is not the default.
+    const char* reg_p2p_env = getenv("HGMM_REG_P2P");
+    const bool reg_no_p2p = !(reg_p2p_env && reg_p2p_env[0] == '1');
     RegXchgView xv = {};
     xv.nranks = 1;
     const bool fused = ctx->nranks > 1 && ctx->p2p_ready && ctx->xwin_reg_off != 0 && tm.nt <= kRegXchgNodes && !reg_no_p2p;

@@ -1,9 +1,8 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-(timeout 400 $TR --master-port 29551 tests/multigpu_worker.py 2>&1 | grep -E "MULTIGPU|P2P|Error|assert|Traceback" | cut -c1-3500) > gpurun_out/r2_mg2_worker.log
-cat gpurun_out/r2_mg2_worker.log
-(timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "overflow or more_nodes" 2>&1 | tail -5 | cut -c1-400)
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+(timeout 400 $TR --master-port 29551 tests/multigpu_worker.py 2>&1 | grep -E "MULTIGPU|P2P|Error|assert|Traceback" | cut -c1-3500) > gpurun_out/r2_mg8_worker.log
+cat gpurun_out/r2_mg8_worker.log
 python - <<'PY' 2>&1 | grep -E "REGMG|rror" | cut -c1-300
 import os, sys, subprocess
 code = r'''
@@ -23,14 +22,14 @@ for _ in range(5):
     dist.barrier()
     rot, t, q, it, _h = eng.register_tree(solver="twist_lstsq", maxiter=20, tol=0.0)
     best = min(best, float(eng.last_timing_ms()[0]))
-if rank == 0: print("REGMG world=%d no_p2p=%s: %d iterations %.3f ms -> %.1f us/iteration" % (world, os.environ.get("HGMM_REG_NO_P2P", "0"), it, best, best * 1e3 / it), flush=True)
+if rank == 0: print("REGMG world=%d reg_p2p=%s: %d iterations %.3f ms -> %.1f us/iteration" % (world, os.environ.get("HGMM_REG_P2P", "0"), it, best, best * 1e3 / it), flush=True)
 eng.comm_destroy(); dist.destroy_process_group()
 '''
 open("/tmp/regmg.py", "w").write(code)
 for v in ("0", "1"):
-    env = dict(os.environ, HGMM_REG_NO_P2P=v)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "2956" + v, "/tmp/regmg.py"], env=env, capture_output=True, text=True)
+    env = dict(os.environ, HGMM_REG_P2P=v)
+    r = subprocess.run(["timeout", "120", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "8", "--master-addr", "127.0.0.1", "--master-port", "2956" + v, "/tmp/regmg.py"], env=env, capture_output=True, text=True)
     print(r.stdout[-600:]); print(r.stderr[-300:])
 PY
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err
 echo "bench rc=$?"

@@ -69,6 +69,10 @@ def main():
     eng.tree_set_model(L, tre["pi"], tre["mu"], tre["cov"])
     rot_s, t_s, q_s, it_s, _ = eng.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
     rot_p, t_p, q_p, it_p, _ = eng.register_tree(solver="procrustes_svd", maxiter=15, tol=1e-9)
+    os.environ["HGMM_REG_P2P"] = "1"       # the opt-in exchange inside the solve kernel (engine.cu reads the switch per call)
+    rot_x, t_x, q_x, it_x, _ = eng.register_tree(solver="twist_lstsq", maxiter=15, tol=1e-6)
+    rot_y, t_y, q_y, it_y, _ = eng.register_tree(solver="procrustes_svd", maxiter=15, tol=1e-9)
+    del os.environ["HGMM_REG_P2P"]
     # ---- flat-mixture registration with a sharded target (model: a J = 100 fit of the sharded source)
     Jr = 100
     mur = X[np.random.default_rng(4).choice(len(X), Jr, replace=False)]
@@ -131,6 +135,8 @@ def main():
             "flat_reg": max(rel_fro(frot, frot1), float(np.abs(ft - ft1).max())),
             "tree_reg_same_model_twist": max(rel_fro(rot_s, rot_s1), float(np.abs(t_s - t_s1).max())),
             "tree_reg_same_model_procrustes": max(rel_fro(rot_p, rot_p1), float(np.abs(t_p - t_p1).max())),
+            "tree_reg_same_model_twist_peer_memory": max(rel_fro(rot_x, rot_s1), float(np.abs(t_x - t_s1).max())) + (0 if it_x == it_s1 else 1),
+            "tree_reg_same_model_procrustes_peer_memory": max(rel_fro(rot_y, rot_p1), float(np.abs(t_y - t_p1).max())) + (0 if it_y == it_p1 else 1),
             "tree_level_root": root(tr, ts), "tree_estep_root": root(tre, tse), "tree_estep_nccl_root": root(tren, tse), "tree_L4_fixed6_root": root(t4, s4),
         }
         soft = {      # converged / deep trees below the root: a point that changes leaf on the last bit of a responsibility moves a small node by
