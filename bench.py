@@ -329,21 +329,23 @@ def main():
     peak_imm, peak_reg, peak_packed = eng.measure_fp32_peak()
     sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
     nominal_fp32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12          # 148 SMs x 128 FMA lanes x 2 flop at the max SM clock
-    roof = {"bound": "hbm", "kernel": "em_flat7_kernel", "achieved": bytes_alg / k_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+    sweep_kernel = "em_flat7_kernel" if os.environ.get("HGMM_FLAT_SWEEP", "")[:1] == "7" else "em_flat8_kernel"
+    roof = {"bound": "hbm", "kernel": sweep_kernel, "achieved": bytes_alg / k_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": bytes_alg / k_avg_s / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
             "avg_launch_us": k_avg_s * 1e6,
             "note": "J=800 makes this sweep FP32-issue bound (52*J/12 = 3467 flop/B >> the ~10 flop/B ridge); see roofline_fp32"}
-    roof32 = {"bound": "fp32", "kernel": "em_flat7_kernel", "achieved": flops_alg / k_avg_s / 1e12, "peak": peak_packed, "unit": "TFLOP/s",
+    roof32 = {"bound": "fp32", "kernel": sweep_kernel, "achieved": flops_alg / k_avg_s / 1e12, "peak": peak_packed, "unit": "TFLOP/s",
               "frac": flops_alg / k_avg_s / 1e12 / peak_packed if peak_packed > 0 else None,
               "peak_nominal": nominal_fp32, "frac_of_nominal": flops_alg / k_avg_s / 1e12 / nominal_fp32,
               "peak_source": "measured live: packed FFMA2 register loop (hgmm_measure_fp32_peak); scalar 3-register FFMA measures "
                              "%.1f, immediate-operand FFMA %.1f TFLOP/s on the same device; nominal = 148 SM x 128 lanes x 2 x %.0f MHz"
                              % (peak_reg, peak_imm, sm_mhz)}
-    prof_json = os.path.join(ROOT, "profiles", "em_flat_traffic.json")
+    prof_name = "em_flat_traffic.json" if sweep_kernel == "em_flat7_kernel" else "r02_em_flat8_traffic.json"
+    prof_json = os.path.join(ROOT, "profiles", prof_name)
     if os.path.exists(prof_json):
         try:
             roof["traffic"] = json.load(open(prof_json)).get("dram_bytes_per_launch")
-            roof["traffic_source"] = "from profiles/em_flat_traffic.json (one `ncu --set full` capture), not measured in this run"
+            roof["traffic_source"] = "from profiles/%s (one `ncu --set full` capture), not measured in this run" % prof_name
         except Exception:
             pass
 

@@ -112,6 +112,8 @@ struct hgmm_ctx {
     int64_t n_total = 0;
     int64_t declared_total = 0;     // hgmm_declare_total_points: > 0 replaces the all-reduce of hgmm_set_points
     DevBuf bx, by, bz, stage;
+    DevBuf sx, sy, sz, sort_scratch;   // the cloud in Morton-cell order (cloud_sort.cu), built on demand for em_flat8_kernel
+    bool sorted_valid = false;
 
     // shared small state
     DevBuf acc;          // doubles: [kAccHdr + count*kMom]
@@ -271,7 +273,8 @@ int hgmm_destroy(hgmm_ctx* ctx) {
                      &ctx->f_covs, &ctx->f_weights, &ctx->f_invcov, &ctx->f_packed, &ctx->labels, &ctx->done_at, &ctx->partial, &ctx->rowaux, &ctx->cref, &ctx->t_pi, &ctx->t_mu, &ctx->t_cov,
                      &ctx->t_cplx, &ctx->t_packed, &ctx->t_init, &ctx->p_group, &ctx->p_tilecnt, &ctx->p_tileoff, &ctx->p_segbase,
                      &ctx->p_seg0, &ctx->p_seg1, &ctx->p_chunkcnt, &ctx->p_chunkoff, &ctx->nchunks, &ctx->current, &ctx->tx, &ctx->ty,
-                     &ctx->tz, &ctx->racc, &ctx->Rt, &ctx->l2buf, &ctx->gbar, &ctx->twin, &ctx->rx, &ctx->ry, &ctx->rz, &ctx->tprof, &ctx->tterm};
+                     &ctx->tz, &ctx->racc, &ctx->Rt, &ctx->l2buf, &ctx->gbar, &ctx->twin, &ctx->rx, &ctx->ry, &ctx->rz, &ctx->tprof, &ctx->tterm,
+                     &ctx->sx, &ctx->sy, &ctx->sz, &ctx->sort_scratch};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < 2; ++i) {
         DevBuf* w[] = {&ctx->wx[i], &ctx->wy[i], &ctx->wz[i], &ctx->wperm[i], &ctx->wpnode[i], &ctx->wslot[i], &ctx->wcpar[i],
@@ -328,6 +331,7 @@ static int upload_cloud(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind
 
 int hgmm_set_points(hgmm_ctx* ctx, const float* xyz, int64_t n, int mem_kind) {
     if (!ctx) return HGMM_ERR_INVALID;
+    ctx->sorted_valid = false;
     int r = upload_cloud(ctx, xyz, n, mem_kind, ctx->bx, ctx->by, ctx->bz, nullptr);
     if (r != HGMM_OK) return r;
     ctx->n = (int)n;
@@ -353,6 +357,41 @@ int hgmm_declare_total_points(hgmm_ctx* ctx, int64_t n_total) {
     if (n_total < 0) FAIL(HGMM_ERR_INVALID, "negative total");
     ctx->declared_total = n_total;
     if (n_total > 0 && ctx->nranks > 1) ctx->n_total = n_total;
+    return HGMM_OK;
+}
+
+// the cloud in Morton-cell order (cloud_sort.cu), built at most once per hgmm_set_points
+static int ensure_sorted_cloud(hgmm_ctx* ctx) {
+    if (ctx->sorted_valid) return HGMM_OK;
+    CK(ctx->sx.ensure((size_t)ctx->n * sizeof(float)));
+    CK(ctx->sy.ensure((size_t)ctx->n * sizeof(float)));
+    CK(ctx->sz.ensure((size_t)ctx->n * sizeof(float)));
+    CK(ctx->sort_scratch.ensure(cloud_sort_scratch_bytes(ctx->n)));
+    CK(launch_cloud_sort(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, ctx->sx.as<float>(),
+                         ctx->sy.as<float>(), ctx->sz.as<float>(), ctx->sort_scratch.p, ctx->stream));
+    ctx->launches += 5;
+    ctx->sorted_valid = true;
+    return HGMM_OK;
+}
+
+int hgmm_sorted_points(hgmm_ctx* ctx, float* out_xyz) {
+    if (!ctx) return HGMM_ERR_INVALID;
+    if (!out_xyz) FAIL(HGMM_ERR_INVALID, "null output");
+    if (ctx->n <= 0) FAIL(HGMM_ERR_STATE, "hgmm_set_points has not been called");
+    CK(cudaSetDevice(ctx->device));
+    int r = ensure_sorted_cloud(ctx);
+    if (r != HGMM_OK) return r;
+    std::vector<float> h((size_t)ctx->n * 3);
+    const size_t nb = (size_t)ctx->n * sizeof(float);
+    CK(cudaMemcpyAsync(h.data(), ctx->sx.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h.data() + ctx->n, ctx->sy.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h.data() + 2 * (size_t)ctx->n, ctx->sz.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->n; ++i) {
+        out_xyz[3 * (size_t)i] = h[i];
+        out_xyz[3 * (size_t)i + 1] = h[(size_t)ctx->n + i];
+        out_xyz[3 * (size_t)i + 2] = h[2 * (size_t)ctx->n + i];
+    }
     return HGMM_OK;
 }
 
@@ -415,6 +454,13 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     } else if (!v1) {
         flat2_plan(ctx->n, Jp, ctx->num_sms, cfg->tile_points == 1, &JT, &W, &Sdiv, &G, &grid, &big);
     }
+    const float *fx = ctx->bx.as<float>(), *fy = ctx->by.as<float>(), *fz = ctx->bz.as<float>();
+    if (v3 && big == 8) {
+        // em_flat8_kernel sums about one origin per CTA: it reads the cloud in Morton-cell order (built once per hgmm_set_points)
+        int rs = ensure_sorted_cloud(ctx);
+        if (rs != HGMM_OK) return rs;
+        fx = ctx->sx.as<float>(); fy = ctx->sy.as<float>(); fz = ctx->sz.as<float>();
+    }
     if (!v1) {
         CK(ctx->partial.ensure((size_t)grid * G * kMom * Jp * sizeof(float)));
         CK(ctx->rowaux.ensure((size_t)grid * G * 2 * sizeof(double)));
@@ -437,7 +483,7 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
             ctx->launches += 1;
         } else {
             if (v3)
-                CK(launch_em_flat3(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, m.cref_blocks, W, Sdiv, G,
+                CK(launch_em_flat3(fx, fy, fz, ctx->n, m, m.cref_blocks, W, Sdiv, G,
                                    grid, big, ctx->partial.as<float>(), ctx->rowaux.as<double>(), done_at + it, s));
             else
                 CK(launch_em_flat2(ctx->bx.as<float>(), ctx->by.as<float>(), ctx->bz.as<float>(), ctx->n, m, m.cref_blocks, JT, W, Sdiv,

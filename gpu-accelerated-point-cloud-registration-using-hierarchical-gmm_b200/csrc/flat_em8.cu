@@ -1,0 +1,445 @@
+// flat_em8.cu -- packed-FP32 fused E+M sweep over a CELL-SORTED cloud: the moment pass is ten FFMA2 per (point, pair).
+//
+// Same contract as em_flat7_kernel (expectationStep + maximizationStep of src/c++/gmm_fit/gmm_kernels.cu:278-350; e_step +
+// m_step of src/python/gmm_waymo/src/gmm_impl.py:90-116) and the same chunk pipeline (wait ; finish ; pass 1 of the next
+// chunk ; arrive ; pass 2 of this chunk, one mbarrier per buffer, no CTA barrier in the steady state).  Pass 1 -- the
+// densities e = 2^(q2 - Cref), d^T A d about the component mean -- is em_flat7's, instruction for instruction.
+//
+// What changes is the moment pass, 59 % of em_flat7's FP32-pipe cycles (17 of its 29 packed operations per pair: gamma,
+// d = x - m again, gamma*d, four adds, six FMAs).  Here the ten sums of a CHUNK (<= 32 points) are taken about one origin o,
+// a point of the chunk, instead of about each component's mean:
+//     psi_p = inv_p * (1, u, v, w, uu, uv, uw, vv, vw, ww),  (u, v, w) = x_p - o          once per POINT, in the finishing step
+//     s_m  += e_pj * psi_p[m]                                                              ten FFMA2 per (point, pair)
+// psi does not depend on the component, so the finishing step (lane = point, already redundant per warp) builds it and parks
+// it in shared memory as duplicated pairs; the moment pass reads it with five broadcast LDS.128.  After the chunk every lane
+// moves its pair's ten sums from o to the component means, delta = m - o,
+//     M1 = S1 - delta S0,   M2_ab = S2_ab - delta_a S1_b - delta_b M1_a           15 FFMA2 + 3 FADD2 per chunk
+// and adds them to the same centred accumulators em_flat7 keeps (10 FADD2): 10.9 packed operations per pair instead of 17,
+// and the partial rows, the reduce / exchange / finalize kernels are untouched.
+//
+// The move cancels (|delta| / sigma)^2 leading digits of the chunk's fp32 sums.  That is why the cloud is sorted by a 16^3
+// Morton cell grid first (cloud_sort.cu, once per hgmm_set_points): the 32 points of a chunk are then neighbours, the
+// components with any weight there have |delta| of a few sigma, and configs[1] after 10 iterations sits at 1.1e-5 of the
+// float64 oracle where em_flat7's arithmetic sits at 5.5e-6 and the same scheme on the unsorted cloud at 6.6e-5 (float32
+// emulation of both, profiles/r02_flat8_numerics.txt).  Sorting changes the summation order, nothing else; the sort is
+// stable, so fits stay bit-reproducible.
+#include "common.cuh"
+#include "kernels.h"
+#include "packed.cuh"
+
+namespace hgmm {
+
+constexpr int kRed8 = 32;               // points per chunk are at most 32 (lane = point in the finishing step)
+
+// dynamic shared memory layout (CH = chunk points, SB = staged points, C = 32 * P):
+//   u64 bars[2] | float red[2][16][32] | float mval[32] | float4 psi[2][32][5] | float4 spts[SB + 8][2] | float2 ebuf[2][CH][C]
+// the rare path's column maxima / shifted sums live in the OTHER buffer's half of red (free while every warp is between
+// finish(c) and pass 1 of chunk c + 1)
+__host__ __device__ inline size_t flat8_fixed_bytes() { return 16 + 2 * 16 * kRed8 * 4 + kRed8 * 4 + 2 * kRed8 * 5 * 16; }
+__host__ __device__ inline size_t flat8_smem_bytes(int CH, int SB, int C) {
+    return flat8_fixed_bytes() + (size_t)(SB + 8) * 32 + (size_t)2 * CH * C * 8;
+}
+
+__device__ __forceinline__ void mbar_arrive8(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait8(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT8_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAIT8_DONE;\n\t"
+        "bra WAIT8_LOOP;\n\t"
+        "WAIT8_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
+
+template <int P>
+__global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                          const float* __restrict__ pz, int n,
+                                                          const PackedComp* __restrict__ packed,
+                                                          const float* __restrict__ cref_blocks, int n_cref, int Jp, int CH,
+                                                          int SB, float* __restrict__ partial, double* __restrict__ rowaux,
+                                                          const int* __restrict__ done_flag, float norm_eps_on) {
+    constexpr int PB = 8;
+    constexpr int C = P * 32;                                              // e columns
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x, W = T >> 5;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                // [2]
+    float* red = reinterpret_cast<float*>(bars + 2);                       // [2][16][32]  partial sums, column-major
+    float* mval = red + 2 * 16 * kRed8;                                    // [32]         rare path: exact maxima
+    float4* psi = reinterpret_cast<float4*>(mval + kRed8);                 // [2][32][5]   inv * monomials, duplicated pairs
+    float4* spts = psi + 2 * kRed8 * 5;                                    // [SB + 8][2]  (x,x,y,y) (z,z,0,0)
+    float2* ebuf = reinterpret_cast<float2*>(spts + (size_t)(SB + 8) * 2); // [2][CH][C]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = Jp >> 5;
+    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const bool rwriter = (lane & 3) == 0;
+    if (tid == 0) {
+        mbar_init(&bars[0], W);
+        mbar_init(&bars[1], W);
+        mbar_fence_init();
+    }
+    const int per = (int)(((long long)n + gridDim.x - 1) / gridDim.x);
+    const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
+    auto stage = [&](int sb0, int cn) {
+        for (int i = tid; i < cn + PB; i += T) {
+            const int src = sb0 + min(i, cn - 1);
+            const float x = px[src], y = py[src], z = pz[src];
+            spts[2 * i] = make_float4(x, x, y, y);
+            spts[2 * i + 1] = make_float4(z, z, 0.f, 0.f);
+        }
+    };
+    // the cloud never changes between EM iterations: the first block is staged BEFORE the programmatic-dependent-launch
+    // wait and overlaps the tail of the previous iteration's reduce + finalize kernel
+    if (hi > lo) stage(lo, min(SB, hi - lo));
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (__ldcg(done_flag)) return;
+
+    // ---- which pair column, and which share of every chunk's batches, this warp sweeps (as em_flat7_kernel)
+    const int full = P == W ? P : (P & ~3);
+    int col = warp, nsplit = 1, sidx = 0;
+    if (warp >= full) {
+        const int r = P - full;
+        nsplit = 4 / r;
+        col = full + (warp - full) / nsplit;
+        sidx = (warp - full) % nsplit;
+    }
+
+    float cref = lane < n_cref ? __ldcg(cref_blocks + lane) : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cref = fmaxf(cref, __shfl_xor_sync(0xffffffffu, cref, o));
+    if (!(cref > kNegBig)) cref = 0.f;
+
+    PairParams k;
+    const bool live0 = col < S, live1 = col + P < S;
+    {
+        const float4* a4 = reinterpret_cast<const float4*>(packed + (live0 ? col * 32 + lane : 0));
+        const float4* b4 = reinterpret_cast<const float4*>(packed + (live1 ? (col + P) * 32 + lane : 0));
+        const float4 a0 = __ldcg(a4), a1 = __ldcg(a4 + 1), a2 = __ldcg(a4 + 2);
+        const float4 b0 = __ldcg(b4), b1 = __ldcg(b4 + 1), b2 = __ldcg(b4 + 2);
+        k.nmx = make_float2(-a0.x, -b0.x);
+        k.nmy = make_float2(-a0.y, -b0.y);
+        k.nmz = make_float2(-a0.z, -b0.z);
+        k.c2 = make_float2(live0 ? a0.w - cref : -INFINITY, live1 ? b0.w - cref : -INFINITY);
+        k.axx = make_float2(a1.x, b1.x);
+        k.ayy = make_float2(a1.y, b1.y);
+        k.azz = make_float2(a1.z, b1.z);
+        k.axy = make_float2(a1.w, b1.w);
+        k.axz = make_float2(a2.x, b2.x);
+        k.ayz = make_float2(a2.y, b2.y);
+    }
+    float2 a[kMom];
+#pragma unroll
+    for (int m = 0; m < kMom; ++m) a[m] = make_float2(0.f, 0.f);
+    double ll = 0.0, nlive = 0.0;                         // warp 0, lane = point of the chunk
+
+    float2* const ecol = ebuf + col * 32 + lane;          // element p of buffer b's column: ecol[(b * CH + p) * C]
+    float* const redcol = red + col * kRed8;              // this column's partial sums: redcol[b * 16 * 32 + p]
+    unsigned g = 0;                                       // chunks done so far: buffer g & 1, mbarrier parity (g >> 1) & 1
+
+    auto pass1 = [&](int c0, int ch, int b) {
+        const int nb = (ch + PB - 1) / PB;
+        const int b_lo = (sidx * nb / nsplit) * PB, b_hi = ((sidx + 1) * nb / nsplit) * PB;
+        for (int bb = b_lo; bb < b_hi; bb += PB) {
+            const float4* sp = spts + 2 * (c0 + bb);
+            float2* eb = ecol + (size_t)(b * CH + bb) * C;
+            float sm[PB];
+            float2 q[PB];
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                const float4 P0 = sp[2 * p], P1 = sp[2 * p + 1];
+                float2 dx, dy, dz;
+                q[p] = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
+            }
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                const float2 e = make_float2(ex2f(q[p].x), ex2f(q[p].y));
+                eb[p * C] = e;
+                sm[p] = e.x + e.y;
+            }
+            reduce_scatter<PB>(sm, lane, false);
+            if (rwriter) redcol[b * 16 * kRed8 + bb + ridx] = sm[0];
+        }
+    };
+
+    for (int sb0 = lo; sb0 < hi; sb0 += SB) {
+        const int cn = min(SB, hi - sb0);
+        if (sb0 != lo) {
+            __syncthreads();                              // the previous block's points are no longer read
+            stage(sb0, cn);
+        }
+        __syncthreads();                                  // points staged (and, the first time, barriers initialised)
+        const int K = (cn + CH - 1) / CH;
+        pass1(0, min(CH, cn), g & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive8(&bars[g & 1]);
+        for (int c = 0; c < K; ++c, ++g) {
+            const int b = g & 1;
+            const int c0 = c * CH;
+            const int ch = min(CH, cn - c0);
+            mbar_wait8(&bars[b], (g >> 1) & 1);
+            // ---------------- finish (every warp, lane = point): fold the P column sums in a fixed order
+            const bool valid = lane < ch;
+            float v = 0.f;
+            {
+                const float* r = red + b * 16 * kRed8 + lane;
+#pragma unroll
+                for (int kk = 0; kk < P; ++kk) v += r[kk * kRed8];
+            }
+            const bool under = valid && !(v >= kUnder3);
+            float iv = (valid && !under) ? __fdividef(1.0f, v) : 0.f;
+            if (valid && !under) {
+                const float lse2 = cref + lg2f(v);
+                float norm2 = lse2;
+                if (norm_eps_on != 0.f) {                    // gmm_impl.py:113  log(sum exp + 1e-8)
+                    const float Mx = fmaxf(lse2, kLog2Eps8);
+                    norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
+                    iv *= ex2f(lse2 - norm2);
+                }
+                if (warp == 0) {
+                    ll += (double)(norm2 * kLn2);
+                    nlive += 1.0;
+                }
+            }
+            const bool any_under = __any_sync(0xffffffffu, under);
+            if (any_under) {
+                // ---------------- rare path: exact per-point maxima for the whole chunk (identical decision in every warp)
+                float* rmax = red + (b ^ 1) * 16 * kRed8;   // the other buffer's sums were consumed by finish(c - 1) of every warp
+                const int nb = (ch + PB - 1) / PB;
+                const int b_lo = (sidx * nb / nsplit) * PB, b_hi = ((sidx + 1) * nb / nsplit) * PB;
+                __syncthreads();                            // every warp is past its finish(c) reads of red (both halves quiescent)
+                for (int bb = b_lo; bb < b_hi; bb += PB) {
+                    const float4* sp = spts + 2 * (c0 + bb);
+                    float mx[PB];
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) {
+                        const float4 P0 = sp[2 * p], P1 = sp[2 * p + 1];
+                        float2 dx, dy, dz;
+                        const float2 q = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
+                        mx[p] = fmaxf(fmaxf(q.x, q.y), kNegBig);
+                    }
+                    reduce_scatter<PB>(mx, lane, true);
+                    if (rwriter) rmax[col * kRed8 + bb + ridx] = mx[0];
+                }
+                __syncthreads();
+                float m = kNegBig;
+#pragma unroll
+                for (int kk = 0; kk < P; ++kk) m = fmaxf(m, rmax[kk * kRed8 + lane]);
+                mval[lane] = m;                           // every warp writes the same values
+                __syncthreads();                          // the maxima are read by everyone before the sums overwrite them
+                for (int bb = b_lo; bb < b_hi; bb += PB) {
+                    const float4* sp = spts + 2 * (c0 + bb);
+                    float2* eb = ecol + (size_t)(b * CH + bb) * C;
+                    float sm[PB];
+                    float2 q[PB];
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) {
+                        const float4 P0 = sp[2 * p], P1 = sp[2 * p + 1];
+                        float2 dx, dy, dz;
+                        q[p] = quad2(k, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y), dx, dy, dz);
+                        const float mp = mval[bb + p];
+                        q[p].x -= mp;
+                        q[p].y -= mp;
+                    }
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) {
+                        const float2 e = make_float2(ex2f(q[p].x), ex2f(q[p].y));
+                        eb[p * C] = e;
+                        sm[p] = e.x + e.y;
+                    }
+                    reduce_scatter<PB>(sm, lane, false);
+                    if (rwriter) rmax[col * kRed8 + bb + ridx] = sm[0];
+                }
+                __syncthreads();
+                float vs = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < P; ++kk) vs += rmax[kk * kRed8 + lane];
+                __syncthreads();                          // ... and the sums before pass 1 of the next chunk reuses the buffer
+                iv = 0.f;
+                if (valid && vs > 0.f && m > kNegBig) {
+                    const float lse2 = cref + m + lg2f(vs);
+                    float norm2 = lse2, scale = 1.0f;
+                    if (norm_eps_on != 0.f) {
+                        const float Mx = fmaxf(lse2, kLog2Eps8);
+                        norm2 = Mx + lg2f(ex2f(lse2 - Mx) + ex2f(kLog2Eps8 - Mx));
+                        scale = ex2f(lse2 - norm2);
+                    }
+                    iv = scale / vs;
+                    if (under && warp == 0) {             // the fast path left only the underflowed points out
+                        ll += (double)(norm2 * kLn2);
+                        nlive += 1.0;
+                    }
+                } else if (valid && under && norm_eps_on != 0.f && warp == 0) {
+                    ll += (double)(kLog2Eps8 * kLn2);      // log(0 + 1e-8)
+                }
+            }
+            // ---------------- psi of this lane's point about the chunk's origin (every warp writes the same values)
+            const float4 O0 = spts[2 * (c0 + (ch >> 1))], O1 = spts[2 * (c0 + (ch >> 1)) + 1];
+            const float ox = O0.x, oy = O0.z, oz = O1.x;
+            {
+                const int sp_i = valid ? c0 + lane : c0;                                    // lanes past the chunk: iv = 0
+                const float4 P0 = spts[2 * sp_i], P1 = spts[2 * sp_i + 1];
+                const float u = P0.x - ox, w2 = P0.z - oy, w3 = P1.x - oz;
+                const float iu = iv * u, iw2 = iv * w2, iw3 = iv * w3;
+                float4* dst = psi + (b * kRed8 + lane) * 5;
+                dst[0] = make_float4(iv, iv, iu, iu);
+                dst[1] = make_float4(iw2, iw2, iw3, iw3);
+                const float uu = iu * u, uv = iu * w2, uw = iu * w3;
+                dst[2] = make_float4(uu, uu, uv, uv);
+                const float vv = iw2 * w2, vw = iw2 * w3;
+                dst[3] = make_float4(uw, uw, vv, vv);
+                const float ww = iw3 * w3;
+                dst[4] = make_float4(vw, vw, ww, ww);
+            }
+            __syncwarp();
+            // ---------------- pass 1 of the next chunk, published before this chunk's moment pass
+            if (c + 1 < K) {
+                pass1(c0 + CH, min(CH, cn - c0 - CH), b ^ 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive8(&bars[b ^ 1]);
+            }
+            // ---------------- pass 2: ten FFMA2 per point of this warp's share of chunk c, sums about the chunk's origin
+            {
+                const int nb = (ch + PB - 1) / PB;
+                const int b_lo = (sidx * nb / nsplit) * PB, p_hi = min(((sidx + 1) * nb / nsplit) * PB, ch);
+                const float2* eb = ecol + (size_t)b * CH * C;
+                const float4* ps = psi + b * kRed8 * 5;
+                float2 sc[kMom];
+#pragma unroll
+                for (int m = 0; m < kMom; ++m) sc[m] = make_float2(0.f, 0.f);
+#pragma unroll 4
+                for (int p = b_lo; p < p_hi; ++p) {
+                    const float2 e = eb[(size_t)p * C];
+                    const float4 s0 = ps[5 * p], s1 = ps[5 * p + 1], s2 = ps[5 * p + 2], s3 = ps[5 * p + 3], s4 = ps[5 * p + 4];
+                    sc[0] = ffma2(e, make_float2(s0.x, s0.y), sc[0]);
+                    sc[1] = ffma2(e, make_float2(s0.z, s0.w), sc[1]);
+                    sc[2] = ffma2(e, make_float2(s1.x, s1.y), sc[2]);
+                    sc[3] = ffma2(e, make_float2(s1.z, s1.w), sc[3]);
+                    sc[4] = ffma2(e, make_float2(s2.x, s2.y), sc[4]);
+                    sc[5] = ffma2(e, make_float2(s2.z, s2.w), sc[5]);
+                    sc[6] = ffma2(e, make_float2(s3.x, s3.y), sc[6]);
+                    sc[7] = ffma2(e, make_float2(s3.z, s3.w), sc[7]);
+                    sc[8] = ffma2(e, make_float2(s4.x, s4.y), sc[8]);
+                    sc[9] = ffma2(e, make_float2(s4.z, s4.w), sc[9]);
+                }
+                // from the chunk's origin to the pair's means: nd = o - m = -delta
+                const float2 ndx = fadd2(k.nmx, make_float2(ox, ox));
+                const float2 ndy = fadd2(k.nmy, make_float2(oy, oy));
+                const float2 ndz = fadd2(k.nmz, make_float2(oz, oz));
+                const float2 m1x = ffma2(ndx, sc[0], sc[1]);
+                const float2 m1y = ffma2(ndy, sc[0], sc[2]);
+                const float2 m1z = ffma2(ndz, sc[0], sc[3]);
+                a[0] = fadd2(a[0], sc[0]);
+                a[1] = fadd2(a[1], m1x);
+                a[2] = fadd2(a[2], m1y);
+                a[3] = fadd2(a[3], m1z);
+                a[4] = fadd2(a[4], ffma2(ndx, m1x, ffma2(ndx, sc[1], sc[4])));      // xx
+                a[5] = fadd2(a[5], ffma2(ndy, m1x, ffma2(ndx, sc[2], sc[5])));      // xy
+                a[6] = fadd2(a[6], ffma2(ndz, m1x, ffma2(ndx, sc[3], sc[6])));      // xz
+                a[7] = fadd2(a[7], ffma2(ndy, m1y, ffma2(ndy, sc[2], sc[7])));      // yy
+                a[8] = fadd2(a[8], ffma2(ndz, m1y, ffma2(ndy, sc[3], sc[8])));      // yz
+                a[9] = fadd2(a[9], ffma2(ndz, m1z, ffma2(ndz, sc[3], sc[9])));      // zz
+            }
+        }
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the reduce + finalize kernel may start launching
+    // ---- warps sharing a column fold their partial moments in a fixed order (the e buffers are free now)
+    __syncthreads();
+    if (nsplit > 1 && sidx > 0) {
+        float2* scratch = ebuf + ((size_t)(col - full) * 3 + (sidx - 1)) * 32 * kMom;
+#pragma unroll
+        for (int m = 0; m < kMom; ++m) scratch[m * 32 + lane] = a[m];
+    }
+    __syncthreads();
+    if (nsplit > 1 && sidx == 0) {
+        for (int s2 = 1; s2 < nsplit; ++s2) {
+            const float2* scratch = ebuf + ((size_t)(col - full) * 3 + (s2 - 1)) * 32 * kMom;
+#pragma unroll
+            for (int m = 0; m < kMom; ++m) a[m] = fadd2(a[m], scratch[m * 32 + lane]);
+        }
+    }
+    // ---- partial rows: partial[row][m][Jp], row = blockIdx
+    if (sidx == 0) {
+        float* dst = partial + (size_t)blockIdx.x * kMom * Jp;
+        if (live0) {
+            const int j = col * 32 + lane;
+#pragma unroll
+            for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].x;
+        }
+        if (live1) {
+            const int j = (col + P) * 32 + lane;
+#pragma unroll
+            for (int m = 0; m < kMom; ++m) dst[(size_t)m * Jp + j] = a[m].y;
+        }
+    }
+    if (warp == 0) {                                      // fixed-order fold of the 32 per-lane log-likelihood sums
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ll += __shfl_xor_sync(0xffffffffu, ll, o);
+            nlive += __shfl_xor_sync(0xffffffffu, nlive, o);
+        }
+        if (lane == 0) {
+            rowaux[2 * blockIdx.x] = ll;
+            rowaux[2 * blockIdx.x + 1] = nlive;
+        }
+    }
+}
+
+int flat5_warps(int P);
+
+// chunk length (multiple of 8, at most 32) and staging block (multiple of 8, at most 512) that fit the shared memory
+static void flat8_shape(int C, int smem_optin, int* CH, int* SB) {
+    int ch = 32;
+    while (ch > 8 && flat8_smem_bytes(ch, 64, C) > (size_t)smem_optin) ch -= 8;
+    long long room = (long long)smem_optin - (long long)flat8_smem_bytes(ch, 0, C);
+    int sb = (int)(room / 32) / 8 * 8;
+    if (sb > 512) sb = 512;
+    if (sb < 8) sb = 8;
+    *CH = ch;
+    *SB = sb;
+}
+
+template <int P>
+static cudaError_t launch8(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
+                           int grid, float* partial, double* rowaux, const int* done_flag, int smem_optin, cudaStream_t s) {
+    static DeviceOnce once;      // one per instantiation P
+    if (once.first()) {
+        cudaError_t e = cudaFuncSetAttribute(em_flat8_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+        if (e != cudaSuccess) return e;
+    }
+    int CH, SB;
+    flat8_shape(P * 32, smem_optin, &CH, &SB);
+    const int W = flat5_warps(P);
+    const float eps_on = m.flavor != HGMM_FLAVOR_CPP ? 1.f : 0.f;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(W * 32);
+    cfg.dynamicSmemBytes = flat8_smem_bytes(CH, SB, P * 32);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, em_flat8_kernel<P>, x, y, z, n, m.packed, cref_blocks, m.Jp / 32, m.Jp, CH, SB, partial, rowaux,
+                              done_flag, eps_on);
+}
+
+cudaError_t launch_em_flat8(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
+                            int P, int grid, float* partial, double* rowaux, const int* done_flag, cudaStream_t s) {
+    const int smem_optin = device_smem_optin();
+#define HGMM_F8(PP) case PP: return launch8<PP>(x, y, z, n, m, cref_blocks, grid, partial, rowaux, done_flag, smem_optin, s);
+    switch (P) {
+        HGMM_F8(5) HGMM_F8(6) HGMM_F8(7) HGMM_F8(8) HGMM_F8(9) HGMM_F8(10) HGMM_F8(11) HGMM_F8(12)
+        HGMM_F8(13) HGMM_F8(14) HGMM_F8(15) HGMM_F8(16)
+        default: return cudaErrorInvalidValue;
+    }
+#undef HGMM_F8
+}
+
+}  // namespace hgmm

@@ -78,6 +78,7 @@ SIGNATURES = {
     "hgmm_p2p_detach": (C.c_int, [_VP]),
     "hgmm_p2p_enabled": (C.c_int, [_VP]),
     "hgmm_measure_fp32_peak": (C.c_int, [_VP, _VP]),
+    "hgmm_sorted_points": (C.c_int, [_VP, _VP]),
     "hgmm_last_timing": (C.c_int, [_VP, _VP]),
     "hgmm_set_profiling": (C.c_int, [_VP, C.c_int]),
 }

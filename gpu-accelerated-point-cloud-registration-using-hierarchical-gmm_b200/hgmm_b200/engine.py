@@ -65,6 +65,12 @@ class Engine:
         self._check(self._lib.hgmm_measure_fp32_peak(self._ctx, L.ptr(out)), "hgmm_measure_fp32_peak")
         return float(out[0]), float(out[1]), float(out[2])
 
+    def sorted_points(self):
+        """-> [n,3] float32: the cloud in the Morton-cell order the J > 512 sweep reads it (csrc/cloud_sort.cu)"""
+        out = np.empty((self.n_points, 3), np.float32)
+        self._check(self._lib.hgmm_sorted_points(self._ctx, L.ptr(out)), "hgmm_sorted_points")
+        return out
+
     @staticmethod
     def _cloud_arg(points):
         """-> (void*, n, mem_kind, keepalive). Accepts numpy [N,3] (host) or a CUDA torch tensor [N,3] fp32 contiguous."""

@@ -236,6 +236,12 @@ int hgmm_p2p_enabled(const hgmm_ctx* ctx);
  * register operands -- the pipe the sweep kernels run on and the non-tensor roofline denominator
  * bench.py reports next to the HBM one */
 int hgmm_measure_fp32_peak(hgmm_ctx* ctx, double* out_tflops);
+/* the cloud of hgmm_set_points in the order the large-mixture sweep (J > 512) reads it: a stable
+ * counting sort by a 16^3 Morton cell grid over the cloud's bounding box (csrc/cloud_sort.cu; the
+ * reference's kernels, gmm_kernels.cu:278-350, take the cloud in file order -- EM sums do not depend
+ * on the order beyond rounding).  out_xyz: host, n x 3 floats.  Diagnostic; builds the order if no
+ * fit has needed it yet. */
+int hgmm_sorted_points(hgmm_ctx* ctx, float* out_xyz);
 /* device time of the last fit/registration call in ms (CUDA events on the context stream):
  * [0] whole enqueue-to-finish loop, [1] sum over the E/M sweep kernel launches alone (only when
  * profiling is on, else 0), [2] number of E/M sweep launches that were timed */

@@ -1,35 +1,38 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-(timeout 400 $TR --master-port 29551 tests/multigpu_worker.py 2>&1 | grep -E "MULTIGPU|P2P|Error|assert|Traceback" | cut -c1-3500) > gpurun_out/r2_mg8_worker.log
-cat gpurun_out/r2_mg8_worker.log
-python - <<'PY' 2>&1 | grep -E "REGMG|rror" | cut -c1-300
-import os, sys, subprocess
-code = r'''
-import os, sys, numpy as np, torch, torch.distributed as dist
+(timeout 500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "cloud_sort or sorted_sweep or staged or config2 or variants_agree or far_points or component_count" 2>&1 | tail -15 | cut -c1-600) > gpurun_out/r2_flat8_tests.log
+cat gpurun_out/r2_flat8_tests.log
+python - <<'PY' 2>&1 | tail -12
+import os, sys, numpy as np, torch
 sys.path.insert(0, "."); sys.path.insert(0, "gpu-accelerated-point-cloud-registration-using-hierarchical-gmm_b200")
 import hgmm_b200
-from hgmm_b200 import hgmm as H, dist as hd
-rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-torch.cuda.set_device(local); dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-S = np.load("tests/golden/bun000_xyz.npy"); T = np.load("tests/golden/bun045_xyz.npy")
-eng = hgmm_b200.Engine(local); hd.attach_communicator(eng)
-init = S[H.reference_init_indices(3)]
-eng.set_points(hd.shuffled_shard(S, rank, world, seed=1), total=len(S)); eng.reg_set_target(hd.shuffled_shard(T, rank, world, seed=2))
-eng.fit_tree(init, 3, ls=20.0, ld=1e-4, sig2=4e-4, ll_mode="estep", want_current=False, want_outputs=False)
-best = 1e9
-for _ in range(5):
-    dist.barrier()
-    rot, t, q, it, _h = eng.register_tree(solver="twist_lstsq", maxiter=20, tol=0.0)
-    best = min(best, float(eng.last_timing_ms()[0]))
-if rank == 0: print("REGMG world=%d reg_p2p=%s: %d iterations %.3f ms -> %.1f us/iteration" % (world, os.environ.get("HGMM_REG_P2P", "0"), it, best, best * 1e3 / it), flush=True)
-eng.comm_destroy(); dist.destroy_process_group()
-'''
-open("/tmp/regmg.py", "w").write(code)
-for v in ("0", "1"):
-    env = dict(os.environ, HGMM_REG_P2P=v)
-    r = subprocess.run(["timeout", "120", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "8", "--master-addr", "127.0.0.1", "--master-port", "2956" + v, "/tmp/regmg.py"], env=env, capture_output=True, text=True)
-    print(r.stdout[-600:]); print(r.stderr[-300:])
+eng = hgmm_b200.Engine(0)
+X = np.load("tests/golden/bun000_xyz.npy")
+for J in (800, 1024, 640):
+    mu0 = X[np.random.default_rng(1).choice(len(X), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J, 1, 1)); w0 = np.full(J, 1 / J, np.float32)
+    eng.set_points(torch.from_numpy(X).cuda())
+    for tile, name in ((8, "em_flat7"), (9, "em_flat8")):
+        eng.set_profiling(True)
+        best, k = 1e9, 1e9
+        for _ in range(6):
+            eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False, tile_points=tile)
+            tm = eng.last_timing_ms(); k = min(k, tm[1] / max(tm[2], 1))
+        eng.set_profiling(False)
+        for _ in range(6):
+            eng.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, want_outputs=False, tile_points=tile)
+            best = min(best, eng.last_timing_ms()[0])
+        print("SWEEPAB J=%d %s: sweep %.2f us/launch, 10-iteration fit %.4f ms" % (J, name, k * 1e3, best), flush=True)
 PY
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err
-echo "bench rc=$?"
+timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1_flat7.json 2> gpurun_out/r2_bench_n1_flat7.err; echo "bench7 rc=$?"
+timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; echo "bench8 rc=$?"
+python - <<'PY'
+import json
+for f in ("gpurun_out/r2_bench_n1.json",):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, "value %.1f ms/step %.4f e2e %.1f sweep %.2f us frac %.3f" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["avg_launch_us"], d["roofline_fp32"]["frac"]))
+    except Exception as e:
+        print(f, "ERR", e)
+PY
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:em_flat8 -s 12 -c 1 -o gpurun_out/r2_flat8 -f python profiles/ncu_target.py flat 800 > gpurun_out/r2_ncu_flat8.log 2>&1; echo "ncu rc=$?"

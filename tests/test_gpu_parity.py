@@ -110,13 +110,14 @@ def test_flat_kernel_variants_agree(engine, bun000, variant, tile):
     assert rel_fro(r["means"], omu) < TOL and rel_fro(r["covs"], ocov) < TOL and rel_fro(r["weights"], ow) < TOL
 
 
-STAGED = [(8, 320), (8, 353), (8, 385), (8, 480), (8, 545), (8, 600), (8, 700), (8, 740), (8, 800), (8, 833), (8, 897), (8, 1024), (6, 160), (6, 161), (6, 320), (6, 545), (6, 800), (6, 1024), (7, 225), (7, 256), (7, 320), (7, 545), (7, 800), (7, 1024)]
+STAGED = [(9, 320), (9, 353), (9, 545), (9, 740), (9, 800), (9, 833), (9, 1024), (8, 320), (8, 353), (8, 385), (8, 480), (8, 545), (8, 600), (8, 700), (8, 740), (8, 800), (8, 833), (8, 897), (8, 1024), (6, 160), (6, 161), (6, 320), (6, 545), (6, 800), (6, 1024), (7, 225), (7, 256), (7, 320), (7, 545), (7, 800), (7, 1024)]
 
 
 @pytest.mark.parametrize("tile,J", STAGED)
 def test_flat_staged_kernel_matches_oracle(engine, bun000, tile, J):
-    """flat_em5.cu / flat_em6.cu (densities staged in shared memory, tile_points = 6: component pair per lane, packed FP32;
-    7: one component per thread): every warp count, ragged J and a cloud whose per-CTA share is not a multiple of the
+    """flat_em5.cu / flat_em6.cu / flat_em7.cu / flat_em8.cu (densities staged in shared memory, tile_points = 6: component pair
+    per lane, packed FP32, CTA barriers; 7: one component per thread; 8: mbarrier chunk pipeline; 9: the same with the moment
+    pass about one origin per CTA over the cell-sorted cloud -- the default from J > 512): every warp count, ragged J and a cloud whose per-CTA share is not a multiple of the
     chunk or of the 8-point batch"""
     from oracle import flat_gmm
     X = bun000[::3][:13001]
@@ -132,7 +133,7 @@ def test_flat_staged_kernel_matches_oracle(engine, bun000, tile, J):
     assert np.array_equal(r["means"], r2["means"]) and np.array_equal(r["covs"], r2["covs"])       # bit-reproducible
 
 
-@pytest.mark.parametrize("tile", [6, 7, 8])
+@pytest.mark.parametrize("tile", [6, 7, 8, 9])
 def test_flat_staged_kernel_small_and_large_clouds(engine, bun000, tile):
     """fewer points than CTAs x 16 (short grid), and more than 512 points per CTA (several staging rounds)"""
     from oracle import flat_gmm
@@ -148,7 +149,7 @@ def test_flat_staged_kernel_small_and_large_clouds(engine, bun000, tile):
         assert rel_fro(r["ll"], oll) < TOL
 
 
-@pytest.mark.parametrize("tile", [6, 7, 8])
+@pytest.mark.parametrize("tile", [6, 7, 8, 9])
 @pytest.mark.parametrize("cov_type", ["diag", "spherical"])
 def test_flat_staged_kernel_py_flavour(engine, bun000, cov_type, tile):
     """gmm_impl.py semantics (log(sum exp + 1e-8), +1e-6 floors) through the staged kernels, J = 260"""
@@ -166,7 +167,7 @@ def test_flat_staged_kernel_py_flavour(engine, bun000, cov_type, tile):
     assert rel_fro(r["ll"], o[4]) < TOL
 
 
-@pytest.mark.parametrize("tile", [6, 7, 8])
+@pytest.mark.parametrize("tile", [6, 7, 8, 9])
 def test_flat_staged_kernel_far_points(engine, tile):
     """the staged kernels' exact (max-shifted) path: 30-60 sigma outliers inside otherwise ordinary chunks"""
     from oracle import flat_gmm
@@ -182,6 +183,52 @@ def test_flat_staged_kernel_far_points(engine, tile):
     ow, omu, ocov, oll = flat_gmm.cpp_fit(X, mu0, 2, sigma0_sq=np.float32(1e-4))
     assert rel_fro(r["weights"], ow) < TOL and rel_fro(r["means"], omu) < TOL
     assert rel_fro(r["covs"], ocov) < TOL and rel_fro(r["ll"], oll) < TOL
+
+
+def _morton_cells(X):
+    """csrc/cloud_sort.cu cell_of, operation for operation in float32"""
+    lo, hi = X.min(axis=0), X.max(axis=0)
+    ext = np.float32(max(float((hi - lo).max()), 1e-30))
+    sc = np.float32(16.0) / ext
+    t = ((X - lo).astype(np.float32) * sc).astype(np.float32)
+    g = np.minimum(np.where(t > 0, np.minimum(t, np.float32(1e6)), 0).astype(np.int64), 15)
+    spread = lambda v: (v & 1) | ((v & 2) << 2) | ((v & 4) << 4) | ((v & 8) << 6)
+    return spread(g[:, 0]) | (spread(g[:, 1]) << 1) | (spread(g[:, 2]) << 2)
+
+
+@pytest.mark.parametrize("n", [1, 255, 257, 40256, 300001])
+def test_cloud_sort_is_a_stable_cell_sort(engine, bun000, n):
+    """the order em_flat8_kernel reads the cloud in: a permutation of the input, cells non-decreasing, input order kept inside a
+    cell (so a fit is a pure function of its input), block boundaries (256-point blocks, several points per thread) included"""
+    rng = np.random.default_rng(n)
+    X = bun000[:n] if n <= len(bun000) else (bun000[rng.integers(0, len(bun000), n)] + rng.normal(0, 1e-3, (n, 3))).astype(np.float32)
+    engine.set_points(X)
+    S = engine.sorted_points()
+    cells = _morton_cells(X)
+    order = np.argsort(cells, kind="stable")
+    assert np.array_equal(S, X[order])
+    engine.set_points(X[::-1].copy())                   # a new cloud invalidates the cached order
+    assert np.array_equal(engine.sorted_points(), X[::-1][np.argsort(cells[::-1], kind="stable")])
+
+
+def test_flat_sorted_sweep_against_the_unsorted_one(engine, bun000):
+    """configs[1] through em_flat7_kernel (moments about each component's mean, file order) and em_flat8_kernel (about one
+    origin per CTA, cell order): both within the tolerance of the float64 oracle, and of each other"""
+    from oracle import c_oracle
+    X, J = bun000, 800
+    mu0 = X[np.random.default_rng(1).choice(len(X), J, replace=False)]
+    cov0 = np.tile(np.eye(3, dtype=np.float32) * np.float32(1e-4), (J, 1, 1))
+    engine.set_points(X)
+    w0 = np.full(J, 1.0 / J, np.float32)
+    r7 = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, tile_points=8)
+    r8 = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10)
+    ow, omu, ocov, oll = c_oracle.flat_fit(X, mu0, 10, np.float32(1e-4))
+    for name, r in (("em_flat7", r7), ("em_flat8", r8)):
+        errs = (rel_fro(r["weights"], ow), rel_fro(r["means"], omu), rel_fro(r["covs"], ocov), rel_fro(r["ll"], oll))
+        print("%s rel_fro (w, mu, cov, ll) = %.2e %.2e %.2e %.2e" % ((name,) + errs))
+        assert max(errs) < TOL, (name, errs)
+    assert rel_fro(r8["means"], r7["means"]) < TOL and rel_fro(r8["covs"], r7["covs"]) < TOL
+    assert not np.array_equal(r8["covs"], r7["covs"])          # the switch really selects two kernels
 
 
 @pytest.mark.parametrize("J", [1, 5, 31, 32, 33, 64, 100, 129, 160, 161, 512, 544, 545])
