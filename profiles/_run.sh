@@ -12,7 +12,7 @@ for J in (800, 1024, 640):
     mu0 = X[np.random.default_rng(1).choice(len(X), J, replace=False)]
     cov0 = np.tile(np.eye(3, dtype=np.float32) * 1e-4, (J, 1, 1)); w0 = np.full(J, 1 / J, np.float32)
     eng.set_points(torch.from_numpy(X).cuda())
-    for tile, name in ((8, "em_flat7"), (9, "em_flat8")):
+    for tile, name in ((8, "em_flat7"), (9, "em_flat8"), (10, "em_flat8_chol")):
         eng.set_profiling(True)
         best, k = 1e9, 1e9
         for _ in range(6):
@@ -25,14 +25,13 @@ for J in (800, 1024, 640):
         print("SWEEPAB J=%d %s: sweep %.2f us/launch, 10-iteration fit %.4f ms" % (J, name, k * 1e3, best), flush=True)
 PY
 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1_flat7.json 2> gpurun_out/r2_bench_n1_flat7.err; echo "bench7 rc=$?"
-timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; echo "bench8 rc=$?"
-python - <<'PY'
+python - <<'PY' > /dev/null
 import json
-for f in ("gpurun_out/r2_bench_n1.json",):
+for f in ():
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, "value %.1f ms/step %.4f e2e %.1f sweep %.2f us frac %.3f" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["avg_launch_us"], d["roofline_fp32"]["frac"]))
     except Exception as e:
         print(f, "ERR", e)
 PY
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:em_flat8 -s 12 -c 1 -o gpurun_out/r2_flat8 -f python profiles/ncu_target.py flat 800 > gpurun_out/r2_ncu_flat8.log 2>&1; echo "ncu rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:em_flat8 -s 12 -c 1 -o gpurun_out/r2_flat8b -f python profiles/ncu_target.py flat 800 > gpurun_out/r2_ncu_flat8.log 2>&1; echo "ncu rc=$?"

@@ -110,14 +110,15 @@ def test_flat_kernel_variants_agree(engine, bun000, variant, tile):
     assert rel_fro(r["means"], omu) < TOL and rel_fro(r["covs"], ocov) < TOL and rel_fro(r["weights"], ow) < TOL
 
 
-STAGED = [(9, 320), (9, 353), (9, 545), (9, 740), (9, 800), (9, 833), (9, 1024), (8, 320), (8, 353), (8, 385), (8, 480), (8, 545), (8, 600), (8, 700), (8, 740), (8, 800), (8, 833), (8, 897), (8, 1024), (6, 160), (6, 161), (6, 320), (6, 545), (6, 800), (6, 1024), (7, 225), (7, 256), (7, 320), (7, 545), (7, 800), (7, 1024)]
+STAGED = [(10, 320), (10, 353), (10, 740), (10, 800), (10, 1024), (9, 320), (9, 353), (9, 545), (9, 740), (9, 800), (9, 833), (9, 1024), (8, 320), (8, 353), (8, 385), (8, 480), (8, 545), (8, 600), (8, 700), (8, 740), (8, 800), (8, 833), (8, 897), (8, 1024), (6, 160), (6, 161), (6, 320), (6, 545), (6, 800), (6, 1024), (7, 225), (7, 256), (7, 320), (7, 545), (7, 800), (7, 1024)]
 
 
 @pytest.mark.parametrize("tile,J", STAGED)
 def test_flat_staged_kernel_matches_oracle(engine, bun000, tile, J):
     """flat_em5.cu / flat_em6.cu / flat_em7.cu / flat_em8.cu (densities staged in shared memory, tile_points = 6: component pair
     per lane, packed FP32, CTA barriers; 7: one component per thread; 8: mbarrier chunk pipeline; 9: the same with the moment
-    pass about one origin per CTA over the cell-sorted cloud -- the default from J > 512): every warp count, ragged J and a cloud whose per-CTA share is not a multiple of the
+    pass about one origin per chunk over the cell-sorted cloud -- the default from J > 512; 10: that with the Cholesky-form density
+    pass): every warp count, ragged J and a cloud whose per-CTA share is not a multiple of the
     chunk or of the 8-point batch"""
     from oracle import flat_gmm
     X = bun000[::3][:13001]
@@ -133,7 +134,7 @@ def test_flat_staged_kernel_matches_oracle(engine, bun000, tile, J):
     assert np.array_equal(r["means"], r2["means"]) and np.array_equal(r["covs"], r2["covs"])       # bit-reproducible
 
 
-@pytest.mark.parametrize("tile", [6, 7, 8, 9])
+@pytest.mark.parametrize("tile", [6, 7, 8, 9, 10])
 def test_flat_staged_kernel_small_and_large_clouds(engine, bun000, tile):
     """fewer points than CTAs x 16 (short grid), and more than 512 points per CTA (several staging rounds)"""
     from oracle import flat_gmm
@@ -149,7 +150,7 @@ def test_flat_staged_kernel_small_and_large_clouds(engine, bun000, tile):
         assert rel_fro(r["ll"], oll) < TOL
 
 
-@pytest.mark.parametrize("tile", [6, 7, 8, 9])
+@pytest.mark.parametrize("tile", [6, 7, 8, 9, 10])
 @pytest.mark.parametrize("cov_type", ["diag", "spherical"])
 def test_flat_staged_kernel_py_flavour(engine, bun000, cov_type, tile):
     """gmm_impl.py semantics (log(sum exp + 1e-8), +1e-6 floors) through the staged kernels, J = 260"""
@@ -167,7 +168,7 @@ def test_flat_staged_kernel_py_flavour(engine, bun000, cov_type, tile):
     assert rel_fro(r["ll"], o[4]) < TOL
 
 
-@pytest.mark.parametrize("tile", [6, 7, 8, 9])
+@pytest.mark.parametrize("tile", [6, 7, 8, 9, 10])
 def test_flat_staged_kernel_far_points(engine, tile):
     """the staged kernels' exact (max-shifted) path: 30-60 sigma outliers inside otherwise ordinary chunks"""
     from oracle import flat_gmm
@@ -222,8 +223,9 @@ def test_flat_sorted_sweep_against_the_unsorted_one(engine, bun000):
     w0 = np.full(J, 1.0 / J, np.float32)
     r7 = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, tile_points=8)
     r8 = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10)
+    r9 = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, tile_points=10)
     ow, omu, ocov, oll = c_oracle.flat_fit(X, mu0, 10, np.float32(1e-4))
-    for name, r in (("em_flat7", r7), ("em_flat8", r8)):
+    for name, r in (("em_flat7", r7), ("em_flat8", r8), ("em_flat8 cholesky-form densities", r9)):
         errs = (rel_fro(r["weights"], ow), rel_fro(r["means"], omu), rel_fro(r["covs"], ocov), rel_fro(r["ll"], oll))
         print("%s rel_fro (w, mu, cov, ll) = %.2e %.2e %.2e %.2e" % ((name,) + errs))
         assert max(errs) < TOL, (name, errs)
