@@ -1,6 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-(timeout 500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "cloud_sort or sorted_sweep or staged or config2 or variants_agree or far_points or component_count" 2>&1 | tail -15 | cut -c1-600) > gpurun_out/r2_flat8_tests.log
+(timeout 500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "sorted_sweep or staged or config2" 2>&1 | tail -15 | cut -c1-600) > gpurun_out/r2_flat8_tests.log
 cat gpurun_out/r2_flat8_tests.log
 python - <<'PY' 2>&1 | tail -12
 import os, sys, numpy as np, torch
@@ -24,7 +24,6 @@ for J in (800, 1024, 640):
             best = min(best, eng.last_timing_ms()[0])
         print("SWEEPAB J=%d %s: sweep %.2f us/launch, 10-iteration fit %.4f ms" % (J, name, k * 1e3, best), flush=True)
 PY
-timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1_flat7.json 2> gpurun_out/r2_bench_n1_flat7.err; echo "bench7 rc=$?"
 python - <<'PY' > /dev/null
 import json
 for f in ():
