@@ -455,7 +455,7 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
         flat2_plan(ctx->n, Jp, ctx->num_sms, cfg->tile_points == 1, &JT, &W, &Sdiv, &G, &grid, &big);
     }
     const float *fx = ctx->bx.as<float>(), *fy = ctx->by.as<float>(), *fz = ctx->bz.as<float>();
-    if (v3 && (big == 8 || big == 9)) {
+    if (v3 && big >= 8 && big <= 11) {
         // em_flat8_kernel sums about one origin per CTA: it reads the cloud in Morton-cell order (built once per hgmm_set_points)
         int rs = ensure_sorted_cloud(ctx);
         if (rs != HGMM_OK) return rs;

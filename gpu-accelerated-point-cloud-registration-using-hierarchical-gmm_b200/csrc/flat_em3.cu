@@ -588,15 +588,15 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
     // ... and flat_em8.cu on top of it: the same pipeline and density pass, the moment pass about one origin per CTA over a
     // cell-sorted cloud (ten FFMA2 per pair instead of seventeen packed operations).  The default from 9 pair columns up;
     // tile_points = 8 or HGMM_FLAT_SWEEP=7 keep em_flat7_kernel, tile_points = 9 selects em_flat8_kernel from 5 columns,
-    // tile_points = 10 its Cholesky-form density pass (big = 9).
-    if (((one_cta_per_sm == 8 || one_cta_per_sm == 9 || one_cta_per_sm == 10) && sdiv >= 5 && sdiv <= 16) ||
+    // tile_points = 10 its Cholesky-form density pass (big = 9), 11 / 12 those two with staggered warps (big = 10 / 11).
+    if ((one_cta_per_sm >= 8 && one_cta_per_sm <= 12 && sdiv >= 5 && sdiv <= 16) ||
         (one_cta_per_sm == 0 && sdiv >= 9 && sdiv <= 16)) {
         static const bool keep7 = getenv("HGMM_FLAT_SWEEP") && getenv("HGMM_FLAT_SWEEP")[0] == '7';
         int ctas = num_sms;
         if ((long long)ctas * 16 > n) ctas = (n + 15) / 16;
         if (ctas < 1) ctas = 1;
         *W = sdiv; *Sdiv = sdiv; *G = 1; *grid = ctas;
-        *big = (one_cta_per_sm == 8 || (one_cta_per_sm == 0 && keep7)) ? 7 : (one_cta_per_sm == 10 ? 9 : 8);
+        *big = (one_cta_per_sm == 8 || (one_cta_per_sm == 0 && keep7)) ? 7 : (one_cta_per_sm >= 10 ? one_cta_per_sm - 1 : 8);
         return;
     }
     if (one_cta_per_sm == 6 && sdiv >= 5 && sdiv <= 16) {
@@ -630,7 +630,8 @@ cudaError_t launch_em_flat3(const float* x, const float* y, const float* z, int 
                             cudaStream_t s) {
     const float eps_on = m.flavor != HGMM_FLAVOR_CPP ? 1.f : 0.f;
     const int ncref = m.Jp / 32;
-    if (big == 8 || big == 9) return launch_em_flat8(x, y, z, n, m, cref_blocks, W, grid, big == 9, partial, rowaux, done_flag, s);
+    if (big >= 8 && big <= 11)      // 8: em_flat8, 9: + Cholesky-form densities, 10 / 11: the same with staggered warps
+        return launch_em_flat8(x, y, z, n, m, cref_blocks, W, grid, (big & 1), big >= 10, partial, rowaux, done_flag, s);
     if (big == 7) return launch_em_flat7(x, y, z, n, m, cref_blocks, W, grid, partial, rowaux, done_flag, s);
     if (big == 6) return launch_em_flat6(x, y, z, n, m, cref_blocks, grid, partial, rowaux, done_flag, s);
     if (big == 5) return launch_em_flat5(x, y, z, n, m, cref_blocks, W, grid, partial, rowaux, done_flag, s);

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
                                                           const PackedComp* __restrict__ packed,
                                                           const float* __restrict__ cref_blocks, int n_cref, int Jp, int CH,
                                                           int SB, float* __restrict__ partial, double* __restrict__ rowaux,
-                                                          const int* __restrict__ done_flag, float norm_eps_on) {
+                                                          const int* __restrict__ done_flag, float norm_eps_on, int stagger) {
     constexpr int PB = 8;
     constexpr int C = P * 32;                                              // e columns (one float4 per lane and point pair)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
     float* const redcol = red + col * kRed8;              // this column's partial sums: redcol[b * 16 * 32 + p]
     const int CH2 = CH >> 1;
     unsigned g = 0;                                       // chunks done so far: buffer g & 1, mbarrier parity (g >> 1) & 1
+    const bool late = stagger != 0 && ((warp >> 2) & 1) != 0;
 
     // log2 density (minus Cref) of the lane's pair at a staged point
     float2 bq1 = make_float2(0.f, 0.f), bq2 = bq1, bq3 = bq1;          // CHOL: b of the chunk being evaluated
@@ -380,14 +381,8 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
                 dst[16] = iw2 * w3; dst[18] = iw3 * w3;    // float4 4: yz, zz
             }
             __syncwarp();
-            // ---------------- pass 1 of the next chunk, published before this chunk's moment pass
-            if (c + 1 < K) {
-                pass1(c0 + CH, min(CH, cn - c0 - CH), b ^ 1);
-                __syncwarp();
-                if (lane == 0) mbar_arrive8(&bars[b ^ 1]);
-            }
             // ---------------- pass 2: ten FFMA2 per component and point PAIR of this warp's share of chunk c
-            {
+            auto pass2 = [&]() {
                 const int nb = (ch + PB - 1) / PB;
                 const int pp_lo = (sidx * nb / nsplit) * (PB / 2);
                 const int pp_hi = (min(((sidx + 1) * nb / nsplit) * PB, ch) + 1) >> 1;      // an odd tail pairs with psi = 0
@@ -429,6 +424,24 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
                 a[7] = fadd2(a[7], ffma2(ndy, m1y, ffma2(ndy, sc[2], sc[7])));      // yy
                 a[8] = fadd2(a[8], ffma2(ndz, m1y, ffma2(ndy, sc[3], sc[8])));      // yz
                 a[9] = fadd2(a[9], ffma2(ndz, m1z, ffma2(ndz, sc[3], sc[9])));      // zz
+            };
+            // ---------------- pass 1 of the next chunk is published before this chunk's moment pass -- except, with `stagger`,
+            //                  in every other warp of a scheduler (warps w and w + 4 share one): those take the moment pass first,
+            //                  so the FFMA2-dense pass of one warp overlaps the MUFU / shuffle tails of its neighbours' pass 1
+            if (!late) {
+                if (c + 1 < K) {
+                    pass1(c0 + CH, min(CH, cn - c0 - CH), b ^ 1);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive8(&bars[b ^ 1]);
+                }
+                pass2();
+            } else {
+                pass2();
+                if (c + 1 < K) {
+                    pass1(c0 + CH, min(CH, cn - c0 - CH), b ^ 1);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive8(&bars[b ^ 1]);
+                }
             }
         }
     }
@@ -492,7 +505,7 @@ static void flat8_shape(int C, int smem_optin, int* CH, int* SB) {
 
 template <int P, bool CHOL>
 static cudaError_t launch8(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
-                           int grid, float* partial, double* rowaux, const int* done_flag, int smem_optin, cudaStream_t s) {
+                           int grid, float* partial, double* rowaux, const int* done_flag, int smem_optin, int stagger, cudaStream_t s) {
     static DeviceOnce once;      // one per instantiation
     if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(em_flat8_kernel<P, CHOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
@@ -513,16 +526,17 @@ static cudaError_t launch8(const float* x, const float* y, const float* z, int n
     cfg.attrs = at;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, em_flat8_kernel<P, CHOL>, x, y, z, n, m.packed, cref_blocks, m.Jp / 32, m.Jp, CH, SB, partial,
-                              rowaux, done_flag, eps_on);
+                              rowaux, done_flag, eps_on, stagger);
 }
 
 cudaError_t launch_em_flat8(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
-                            int P, int grid, int chol, float* partial, double* rowaux, const int* done_flag, cudaStream_t s) {
+                            int P, int grid, int chol, int stagger, float* partial, double* rowaux, const int* done_flag,
+                            cudaStream_t s) {
     const int smem_optin = device_smem_optin();
 #define HGMM_F8(PP)                                                                                                            \
     case PP:                                                                                                                   \
-        return chol ? launch8<PP, true>(x, y, z, n, m, cref_blocks, grid, partial, rowaux, done_flag, smem_optin, s)           \
-                    : launch8<PP, false>(x, y, z, n, m, cref_blocks, grid, partial, rowaux, done_flag, smem_optin, s);
+        return chol ? launch8<PP, true>(x, y, z, n, m, cref_blocks, grid, partial, rowaux, done_flag, smem_optin, stagger, s)  \
+                    : launch8<PP, false>(x, y, z, n, m, cref_blocks, grid, partial, rowaux, done_flag, smem_optin, stagger, s);
     switch (P) {
         HGMM_F8(5) HGMM_F8(6) HGMM_F8(7) HGMM_F8(8) HGMM_F8(9) HGMM_F8(10) HGMM_F8(11) HGMM_F8(12)
         HGMM_F8(13) HGMM_F8(14) HGMM_F8(15) HGMM_F8(16)

@@ -139,7 +139,8 @@ cudaError_t launch_em_flat7(const float* x, const float* y, const float* z, int 
 
 // flat_em8.cu (flat_em7's density pass; the moment pass about one origin per CTA, ten FFMA2 per pair; needs a cell-sorted cloud)
 cudaError_t launch_em_flat8(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
-                            int P, int grid, int chol, float* partial, double* rowaux, const int* done_flag, cudaStream_t s);
+                            int P, int grid, int chol, int stagger, float* partial, double* rowaux, const int* done_flag,
+                            cudaStream_t s);
 // cloud_sort.cu: stable counting sort of a cloud by a 16^3 Morton cell grid (scratch: cloud_sort_scratch_bytes(n))
 size_t cloud_sort_scratch_bytes(int64_t n);
 cudaError_t launch_cloud_sort(const float* x, const float* y, const float* z, int64_t n, float* sx, float* sy, float* sz,
