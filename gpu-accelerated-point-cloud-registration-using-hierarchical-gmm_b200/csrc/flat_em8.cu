@@ -36,6 +36,21 @@
 namespace hgmm {
 
 constexpr int kRed8 = 32;               // points per chunk are at most 32 (lane = point in the finishing step)
+
+// -DHGMM_FLAT8_PROF (make prof -> build/libhgmm_prof.so, never the shipped library): every warp accumulates clock64() per phase
+// -- 0 barrier wait, 1 finish + psi, 2 density pass, 3 moment pass + re-centring, 4 prologue, 5 epilogue -- read back by
+// profiles/probe_flat8_phases.py through hgmm_debug_flat8_prof
+#ifdef HGMM_FLAT8_PROF
+__device__ unsigned long long g_f8prof[148 * 16 * 8];
+#define F8T(i)                          \
+    {                                   \
+        const long long t_ = clock64(); \
+        f8p[i] += t_ - f8t;             \
+        f8t = t_;                       \
+    }
+#else
+#define F8T(i)
+#endif
 constexpr int kMaxChunks8 = 64;         // chunks per staging block (SB <= 512, CH >= 8)
 
 // dynamic shared memory layout (CH = chunk points, SB = staged points, C = 32 * P):
@@ -107,6 +122,9 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
     float4* ebuf = spts + (size_t)(SB + 8) * 2;                            // [2][CH/2][C] (eA_p, eA_p+1, eB_p, eB_p+1)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef HGMM_FLAT8_PROF
+    long long f8p[6] = {0, 0, 0, 0, 0, 0}, f8t = clock64();
+#endif
     const int S = Jp >> 5;
     const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     const bool rwriter = (lane & 3) == 0;
@@ -262,15 +280,18 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
             stage(sb0, cn);
         }
         __syncthreads();                                  // points staged (and, the first time, barriers initialised)
+        F8T(4)
         const int K = (cn + CH - 1) / CH;
         pass1(0, min(CH, cn), g & 1);
         __syncwarp();
         if (lane == 0) mbar_arrive8(&bars[g & 1]);
+        F8T(2)
         for (int c = 0; c < K; ++c, ++g) {
             const int b = g & 1;
             const int c0 = c * CH;
             const int ch = min(CH, cn - c0);
             mbar_wait8(&bars[b], (g >> 1) & 1);
+            F8T(0)
             // ---------------- finish (every warp, lane = point): fold the P column sums in a fixed order
             const bool valid = lane < ch;
             float v = 0.f;
@@ -381,6 +402,7 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
                 dst[16] = iw2 * w3; dst[18] = iw3 * w3;    // float4 4: yz, zz
             }
             __syncwarp();
+            F8T(1)
             // ---------------- pass 2: ten FFMA2 per component and point PAIR of this warp's share of chunk c
             auto pass2 = [&]() {
                 const int nb = (ch + PB - 1) / PB;
@@ -434,14 +456,18 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
                     __syncwarp();
                     if (lane == 0) mbar_arrive8(&bars[b ^ 1]);
                 }
+                F8T(2)
                 pass2();
+                F8T(3)
             } else {
                 pass2();
+                F8T(3)
                 if (c + 1 < K) {
                     pass1(c0 + CH, min(CH, cn - c0 - CH), b ^ 1);
                     __syncwarp();
                     if (lane == 0) mbar_arrive8(&bars[b ^ 1]);
                 }
+                F8T(2)
             }
         }
     }
@@ -487,6 +513,11 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
             rowaux[2 * blockIdx.x + 1] = nlive;
         }
     }
+#ifdef HGMM_FLAT8_PROF
+    F8T(5)
+    if (lane == 0 && blockIdx.x < 148 && warp < 16)
+        for (int i = 0; i < 6; ++i) g_f8prof[(blockIdx.x * 16 + warp) * 8 + i] = (unsigned long long)f8p[i];
+#endif
 }
 
 int flat5_warps(int P);
@@ -546,3 +577,9 @@ cudaError_t launch_em_flat8(const float* x, const float* y, const float* z, int 
 }
 
 }  // namespace hgmm
+
+#ifdef HGMM_FLAT8_PROF
+extern "C" int hgmm_debug_flat8_prof(unsigned long long* out) {      // 148 x 16 x 8 counters of the last launch on the current device
+    return (int)cudaMemcpyFromSymbol(out, hgmm::g_f8prof, sizeof(unsigned long long) * 148 * 16 * 8);
+}
+#endif
