@@ -450,7 +450,7 @@ int hgmm_fit_flat(hgmm_ctx* ctx, const hgmm_flat_config* cfg, const float* init_
     const int tile = flat_pick_tile(ctx->n, ctx->num_sms, cfg->tile_points);
     int JT = 1, W = 8, Sdiv = 1, G = 1, grid = 1, big = 0;
     if (v3) {
-        flat3_plan(ctx->n, Jp, ctx->num_sms, (cfg->tile_points >= 1 && cfg->tile_points <= 8) ? cfg->tile_points : 0, &W, &Sdiv, &G, &grid, &big);
+        flat3_plan(ctx->n, Jp, ctx->num_sms, (cfg->tile_points >= 1 && cfg->tile_points <= 12) ? cfg->tile_points : 0, &W, &Sdiv, &G, &grid, &big);
     } else if (!v1) {
         flat2_plan(ctx->n, Jp, ctx->num_sms, cfg->tile_points == 1, &JT, &W, &Sdiv, &G, &grid, &big);
     }
