@@ -29,6 +29,7 @@
 // CHOL = true additionally evaluates the density pass in Cholesky form about the chunk's origin: -A = L L^T,
 //     r = L^T u + b,  b = L^T (o - m) once per chunk,   e = 2^-(r1^2 + r2^2 + r3^2 + (Cref - c2))       9 FFMA2 per pair
 // instead of the 12 of d^T A d (the points are staged relative to their chunk's origin; Cref - c2 >= 0 is the fourth square).
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 #include "packed.cuh"
@@ -52,6 +53,7 @@ __device__ unsigned long long g_f8prof[148 * 16 * 8];
 #define F8T(i)
 #endif
 constexpr int kMaxChunks8 = 64;         // chunks per staging block (SB <= 512, CH >= 8)
+constexpr unsigned kLightSleepNs = 0;   // sleep of the left-over column's warps before they poll a chunk barrier (0 = poll at once)
 
 // dynamic shared memory layout (CH = chunk points, SB = staged points, C = 32 * P):
 //   u64 bars[2] | float red[2][16][32] | float mval[32] | float4 orig[64] | float4 psi[2][16][5] | float4 spts[SB + 8][2]
@@ -88,17 +90,22 @@ struct CholParams {
     float2 l11, l21, l31, l22, l32, l33;       // r1 = l11 u + l21 v + l31 w + b1, r2 = l22 v + l32 w + b2, r3 = l33 w + b3
 };
 
+// 1/sqrt(t) for t > 0: MUFU.RSQ seed (2^-22) and one float64 Newton step (2^-43) -- no DSQRT / DDIV sequences in the prologue
+__device__ __forceinline__ double rsqrt_nr(double t) {
+    const double y = (double)rsqrtf((float)t);
+    return y * (1.5 - 0.5 * t * y * y);
+}
 // -A (packed: diagonal, doubled off-diagonals) = L L^T in float64, a non-positive pivot zeroes its row (flat direction)
 __device__ __forceinline__ void chol_of_minus_a(float axx, float ayy, float azz, float axy, float axz, float ayz, float* l) {
     const double mxx = -(double)axx, myy = -(double)ayy, mzz = -(double)azz;
     const double mxy = -0.5 * (double)axy, mxz = -0.5 * (double)axz, myz = -0.5 * (double)ayz;
-    const double l11 = mxx > 0.0 ? sqrt(mxx) : 0.0, i11 = l11 > 0.0 ? 1.0 / l11 : 0.0;
+    const double i11 = mxx > 1e-300 ? rsqrt_nr(mxx) : 0.0, l11 = mxx * i11;
     const double l21 = mxy * i11, l31 = mxz * i11;
     double t = myy - l21 * l21;
-    const double l22 = t > 0.0 ? sqrt(t) : 0.0, i22 = l22 > 0.0 ? 1.0 / l22 : 0.0;
+    const double i22 = t > 1e-300 ? rsqrt_nr(t) : 0.0, l22 = t * i22;
     const double l32 = (myz - l31 * l21) * i22;
     t = mzz - l31 * l31 - l32 * l32;
-    const double l33 = t > 0.0 ? sqrt(t) : 0.0;
+    const double l33 = t > 1e-300 ? t * rsqrt_nr(t) : 0.0;
     l[0] = (float)l11; l[1] = (float)l21; l[2] = (float)l31; l[3] = (float)l22; l[4] = (float)l32; l[5] = (float)l33;
 }
 
@@ -108,7 +115,8 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
                                                           const PackedComp* __restrict__ packed,
                                                           const float* __restrict__ cref_blocks, int n_cref, int Jp, int CH,
                                                           int SB, float* __restrict__ partial, double* __restrict__ rowaux,
-                                                          const int* __restrict__ done_flag, float norm_eps_on, int stagger) {
+                                                          const int* __restrict__ done_flag, float norm_eps_on, int stagger,
+                                                          unsigned light_sleep_ns) {
     constexpr int PB = 8;
     constexpr int C = P * 32;                                              // e columns (one float4 per lane and point pair)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -290,6 +298,9 @@ __global__ void __launch_bounds__(512, 1) em_flat8_kernel(const float* __restric
             const int b = g & 1;
             const int c0 = c * CH;
             const int ch = min(CH, cn - c0);
+            // the warps that share the left-over column idle ~3/4 of a chunk: they sleep through most of it instead of polling
+            // (a poll is four instructions every ~32 cycles -- an eighth of the scheduler's issue slots)
+            if (nsplit > 1 && light_sleep_ns != 0u) __nanosleep(light_sleep_ns);
             mbar_wait8(&bars[b], (g >> 1) & 1);
             F8T(0)
             // ---------------- finish (every warp, lane = point): fold the P column sums in a fixed order
@@ -546,6 +557,8 @@ static cudaError_t launch8(const float* x, const float* y, const float* z, int n
     flat8_shape(P * 32, smem_optin, &CH, &SB);
     const int W = flat5_warps(P);
     const float eps_on = m.flavor != HGMM_FLAVOR_CPP ? 1.f : 0.f;
+    const char* sl = getenv("HGMM_FLAT8_SLEEP_NS");      // A/B switch (read per launch); default: see launch_em_flat8
+    const unsigned light_sleep_ns = sl ? (unsigned)atoi(sl) : kLightSleepNs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(W * 32);
@@ -557,7 +570,7 @@ static cudaError_t launch8(const float* x, const float* y, const float* z, int n
     cfg.attrs = at;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, em_flat8_kernel<P, CHOL>, x, y, z, n, m.packed, cref_blocks, m.Jp / 32, m.Jp, CH, SB, partial,
-                              rowaux, done_flag, eps_on, stagger);
+                              rowaux, done_flag, eps_on, stagger, light_sleep_ns);
 }
 
 cudaError_t launch_em_flat8(const float* x, const float* y, const float* z, int n, const FlatModel& m, const float* cref_blocks,
