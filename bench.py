@@ -329,7 +329,7 @@ def main():
     peak_imm, peak_reg, peak_packed = eng.measure_fp32_peak()
     sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
     nominal_fp32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12          # 148 SMs x 128 FMA lanes x 2 flop at the max SM clock
-    sweep_kernel = "em_flat7_kernel" if os.environ.get("HGMM_FLAT_SWEEP", "")[:1] == "7" else "em_flat8_kernel"
+    sweep_kernel = "em_flat8_kernel" if os.environ.get("HGMM_FLAT_SWEEP", "")[:1] in ("8", "9") else "em_flat7_kernel"
     roof = {"bound": "hbm", "kernel": sweep_kernel, "achieved": bytes_alg / k_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": bytes_alg / k_avg_s / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
             "avg_launch_us": k_avg_s * 1e6,

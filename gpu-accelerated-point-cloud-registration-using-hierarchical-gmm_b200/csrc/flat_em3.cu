@@ -585,18 +585,22 @@ void flat3_plan(int n, int Jp, int num_sms, int one_cta_per_sm, int* W, int* Sdi
     // shared-memory staged chunks with a barrier-free chunk pipeline (flat_em7.cu), one CTA per SM: the default from 9
     // pair columns up (J > 512; 10-iteration fit of configs[1]: 0.582 ms vs 0.637 for flat_em5, 0.700 for the per-batch
     // barrier kernel; J = 1024: 0.635 / 0.721 / 0.719; J = 640: 0.498 / 0.535 / 0.580 -- profiles/r01_flat_kernel_variants.json)
-    // ... and flat_em8.cu on top of it: the same pipeline and density pass, the moment pass about one origin per CTA over a
-    // cell-sorted cloud (ten FFMA2 per pair instead of seventeen packed operations).  The default from 9 pair columns up;
-    // tile_points = 8 or HGMM_FLAT_SWEEP=7 keep em_flat7_kernel, tile_points = 9 selects em_flat8_kernel from 5 columns,
-    // tile_points = 10 its Cholesky-form density pass (big = 9), 11 / 12 those two with staggered warps (big = 10 / 11).
+    // flat_em8.cu on top of it -- the same pipeline, the moment pass about one origin per chunk over a cell-sorted cloud (ten
+    // FFMA2 per pair instead of seventeen packed operations), optionally the density pass in Cholesky form (9 instead of 12) and
+    // a staggered pass order -- executes 20-30 % fewer FP32-pipe instructions and is NOT faster (configs[1]: 57.3 / 55.5 us per
+    // sweep against em_flat7's 57.0; J = 1024: 63.3 / 62.5 against 61.4 -- profiles/r02_flat_sweep_ab.txt): the sweep is bound by
+    // the latency of each warp's own instruction stream at four 128-register warps per scheduler, not by a pipe.
+    // It stays selectable: tile_points = 9 em_flat8, 10 + Cholesky-form densities, 11 / 12 those two staggered;
+    // HGMM_FLAT_SWEEP=8 / 9 make 9 / 10 the default from 9 pair columns up.
     if ((one_cta_per_sm >= 8 && one_cta_per_sm <= 12 && sdiv >= 5 && sdiv <= 16) ||
         (one_cta_per_sm == 0 && sdiv >= 9 && sdiv <= 16)) {
-        static const bool keep7 = getenv("HGMM_FLAT_SWEEP") && getenv("HGMM_FLAT_SWEEP")[0] == '7';
+        static const int env_sweep = getenv("HGMM_FLAT_SWEEP") ? atoi(getenv("HGMM_FLAT_SWEEP")) : 7;
         int ctas = num_sms;
         if ((long long)ctas * 16 > n) ctas = (n + 15) / 16;
         if (ctas < 1) ctas = 1;
         *W = sdiv; *Sdiv = sdiv; *G = 1; *grid = ctas;
-        *big = (one_cta_per_sm == 8 || (one_cta_per_sm == 0 && keep7)) ? 7 : (one_cta_per_sm >= 10 ? one_cta_per_sm - 1 : 8);
+        if (one_cta_per_sm == 0) *big = (env_sweep == 8 || env_sweep == 9) ? env_sweep : 7;
+        else *big = one_cta_per_sm == 8 ? 7 : one_cta_per_sm - 1;
         return;
     }
     if (one_cta_per_sm == 6 && sdiv >= 5 && sdiv <= 16) {

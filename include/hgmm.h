@@ -76,11 +76,13 @@ typedef struct hgmm_flat_config {
     float tol;                     /* PY flavour: stop when |d mean-log-lik| < tol; CPP flavour ignores it */
     int32_t sigma_bug;             /* CPP flavour only: reproduce gmm_kernels.cu:97-103 (d^T Sigma d) */
     int32_t tile_points;           /* 0 = auto.  64/128/256/512: points per CTA tile of the first-generation kernel (reserved = 1).
-                                    * 1..8: A/B switch between builds of the packed sweep (profiles/variants_probe.py, tests):
+                                    * 1..12: A/B switch between builds of the packed sweep (profiles/variants_probe.py, tests):
                                     * 1 one register-rich CTA per SM, 2 two CTAs per SM, 3 two teams of 4 components per lane,
                                     * 4 per-batch mbarrier pipeline, 5 152-register build, 6 staged chunks with CTA barriers
                                     * (flat_em5.cu), 7 one component per thread (flat_em6.cu), 8 staged chunks with the
-                                    * barrier-free pipeline (flat_em7.cu; what 0 selects for J > 512) */
+                                    * barrier-free pipeline (flat_em7.cu; what 0 selects for J > 512), 9 that pipeline with the
+                                    * moment pass about one origin per chunk of the cell-sorted cloud (flat_em8.cu), 10 its
+                                    * Cholesky-form density pass, 11 / 12 = 9 / 10 with a staggered pass order */
     int32_t reserved;              /* kernel variant: 0 = default (packed-FP32 sweep), 1 = first-generation two-phase kernel, 2 = scalar single-evaluation kernel, 3 = packed sweep with separate reduce / finalize launches */
 } hgmm_flat_config;
 

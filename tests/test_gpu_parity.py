@@ -117,7 +117,7 @@ STAGED = [(11, 353), (11, 800), (12, 740), (12, 1024), (10, 320), (10, 353), (10
 def test_flat_staged_kernel_matches_oracle(engine, bun000, tile, J):
     """flat_em5.cu / flat_em6.cu / flat_em7.cu / flat_em8.cu (densities staged in shared memory, tile_points = 6: component pair
     per lane, packed FP32, CTA barriers; 7: one component per thread; 8: mbarrier chunk pipeline; 9: the same with the moment
-    pass about one origin per chunk over the cell-sorted cloud -- the default from J > 512; 10: that with the Cholesky-form density
+    pass about one origin per chunk over the cell-sorted cloud; 10: that with the Cholesky-form density
     pass; 11 / 12: 9 / 10 with every other warp of a scheduler taking the moment pass first): every warp count, ragged J and a cloud whose per-CTA share is not a multiple of the
     chunk or of the 8-point batch"""
     from oracle import flat_gmm
@@ -222,7 +222,7 @@ def test_flat_sorted_sweep_against_the_unsorted_one(engine, bun000):
     engine.set_points(X)
     w0 = np.full(J, 1.0 / J, np.float32)
     r7 = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, tile_points=8)
-    r8 = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10)
+    r8 = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, tile_points=9)
     r9 = engine.fit_flat(mu0, cov0, w0, cov_type="full", max_iter=10, tile_points=10)
     ow, omu, ocov, oll = c_oracle.flat_fit(X, mu0, 10, np.float32(1e-4))
     for name, r in (("em_flat7", r7), ("em_flat8", r8), ("em_flat8 cholesky-form densities", r9)):
